@@ -1,0 +1,295 @@
+#!/usr/bin/env python
+"""
+bench.py -- KernelMF SGD rating-updates/s on synthetic MovieLens/Netflix-shaped ratings.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--workload ml-20m|netflix|ml-1m|ml-100k]
+                    [--impl ours|reference] [--uniform]
+
+A "step" is one epoch of KernelMF.fit's loop on the workload: the stratified SGD kernel over all
+ratings plus the per-epoch train-RMSE pass (what `_sgd` does every epoch,
+kernel_matrix_factorization.py:369-440).  `value` = ratings x K / device time (CUDA events, max
+over ranks), inputs resident in HBM.  `e2e` = the same metric through the host-buffer C-ABI call
+`mfk_kmf_sgd_host` (pinned host arrays in, H2D, plan build, n_epochs epochs + RMSE, D2H out).
+`roofline` is for the SGD kernel alone (algorithmic bytes (16F+28) per update).  `cpu_baseline`
+times the fp64 oracle port of the reference's `_sgd` (shuffle + updates + RMSE) on a bounded
+sample on one host core (the reference is single-threaded numba).
+
+--impl reference prints the same line for the CPU arm only (rank 0; other ranks exit).
+"""
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+import numpy as np  # noqa: E402
+
+WORKLOADS = {
+    # name: (shape key, n_factors, n_epochs of the config, lr, reg)
+    "ml-100k": ("ml-100k", 100, 20, 0.001, 0.005),
+    "ml-1m": ("ml-1m", 100, 20, 0.001, 0.005),
+    "ml-20m": ("ml-20m", 128, 20, 0.001, 0.005),
+    "netflix": ("netflix", 256, 20, 0.001, 0.005),
+}
+
+
+def load_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled during the timed region."""
+
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index=0):
+        self.rows, self.proc, self.gpu_index = [], None, gpu_index
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                          "-lms", "100", "-i", str(self.gpu_index)], stdout=subprocess.PIPE, text=True)
+            threading.Thread(target=self._read, daemon=True).start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if self.proc is None:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        time.sleep(0.15)
+        self.proc.terminate()
+        sm = [float(r[1]) for r in self.rows if len(r) >= 9 and r[1].replace(".", "").isdigit()]
+        mx = [float(r[2]) for r in self.rows if len(r) >= 9 and r[2].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 9:
+                for name, v in zip(["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"], r[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def gen_workload(name, device, uniform=False, seed=None):
+    from matrix_factorization_b200.data import SHAPES, synth_ratings_torch
+
+    shape, F, n_epochs, lr, reg = WORKLOADS[name]
+    U, I, N, step, _ = SHAPES[shape]
+    seed = 1000 + list(SHAPES).index(shape) if seed is None else seed
+    u, i, r = synth_ratings_torch(U, I, N, seed, device, grid_step=step, uniform=uniform)
+    return dict(U=U, I=I, N=N, F=F, n_epochs=n_epochs, lr=lr, reg=reg, u=u, i=i, r=r)
+
+
+def cpu_baseline(wl, sample_ratings, seed=7):
+    """fp64 oracle port of the reference `_sgd` (shuffle + sequential updates + RMSE pass) on a bounded
+    sample of the workload, one host core."""
+    from oracle import oracle as orc
+
+    orc.lib()
+    n = min(sample_ratings, wl["N"])
+    u = wl["u"][:n].cpu().numpy()
+    i = wl["i"][:n].cpu().numpy()
+    r = wl["r"][:n].cpu().numpy().astype(np.float64)
+    rng = np.random.default_rng(seed)
+    P = rng.normal(0, 0.1, (wl["U"], wl["F"]))
+    Q = rng.normal(0, 0.1, (wl["I"], wl["F"]))
+    bu, bi = np.zeros(wl["U"]), np.zeros(wl["I"])
+    mu = float(r.mean())
+    orc.kmf_sgd("linear", u[:1000], i[:1000], r[:1000], mu, bu, bi, P, Q, 1, wl["lr"], wl["reg"])  # warm caches
+    t0 = time.perf_counter()
+    orc.kmf_sgd("linear", u, i, r, mu, bu, bi, P, Q, 1, wl["lr"], wl["reg"])
+    dt = time.perf_counter() - t0
+    return n / dt, dt, n
+
+
+def run_reference_arm(args):
+    """CPU arm: the oracle port of the reference's `_sgd` on the box's host cores (the reference is
+    single-threaded numba; its Python sources do not travel, so the C port stands in -- kind 'port')."""
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    import torch
+
+    dev = torch.device("cuda", 0) if torch.cuda.is_available() else torch.device("cpu")
+    wl = gen_workload(args.workload, dev, uniform=args.uniform)
+    sample = 2_000_000 if wl["F"] <= 128 else 1_000_000
+    rates, total = [], 0.0
+    for s in range(args.warmup + args.steps):
+        rate, dt, n = cpu_baseline(wl, sample, seed=7 + s)
+        if s >= args.warmup:
+            rates.append(rate)
+            total += dt
+    v = float(np.mean(rates))
+    line = {
+        "impl": "reference", "metric": "KernelMF SGD rating-updates/s", "value": v, "unit": "rating-updates/s",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * total / max(1, args.steps),
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": workload_name(args), "n_factors": wl["F"], "kernel": "linear",
+                   "sample": f"first {sample} ratings of the workload, 1 epoch per step"},
+        "cpu_baseline": {"value": v, "unit": "rating-updates/s", "cores": 1, "kind": "port",
+                         "sample": f"{sample} ratings x 1 epoch (shuffle + updates + RMSE pass), fp64, 1 thread of {os.cpu_count()}"},
+        "e2e": {"value": v, "unit": "rating-updates/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line))
+
+
+def workload_name(args):
+    shape = WORKLOADS[args.workload][0]
+    from matrix_factorization_b200.data import SHAPES
+
+    U, I, N, _, _ = SHAPES[shape]
+    return (f"KernelMF linear n_factors={WORKLOADS[args.workload][1]} on synthetic {shape} shape "
+            f"({U} users, {I} items, {N} ratings, {'uniform' if args.uniform else 'Zipf'} pairs)")
+
+
+def e2e_host_call(wl, n_epochs):
+    """One `_sgd`-equivalent call through the C ABI with pinned HOST buffers (H2D + plan + epochs + D2H)."""
+    import ctypes as C
+    import torch
+    from matrix_factorization_b200 import _lib
+
+    L = _lib.lib()
+    F, U, I, N = wl["F"], wl["U"], wl["I"], wl["N"]
+    hu, hi, hr = wl["u"].cpu().pin_memory(), wl["i"].cpu().pin_memory(), wl["r"].cpu().pin_memory()
+    g = torch.Generator().manual_seed(5)
+    hP = (torch.randn(U, F, generator=g) * 0.1).pin_memory()
+    hQ = (torch.randn(I, F, generator=g) * 0.1).pin_memory()
+    hbu, hbi = torch.zeros(U).pin_memory(), torch.zeros(I).pin_memory()
+    rm = np.zeros(n_epochs, dtype=np.float64)
+    mu = float(wl["r"].double().mean().item())
+    opts = _lib.PlanOpts(0, 0, F, 0)
+
+    def call():
+        _lib.check(L.mfk_kmf_sgd_host(0, _lib.ptr(hu), _lib.ptr(hi), _lib.ptr(hr), N, U, I, _lib.ptr(hP), _lib.ptr(hQ),
+                                      _lib.ptr(hbu), _lib.ptr(hbi), F, F, mu, n_epochs, wl["lr"], wl["reg"], 1.0 / F,
+                                      0.0, 5.0, 1, 1, C.byref(opts), _lib.ptr(rm), None))
+
+    call()  # warm-up (first-touch allocations, module load)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    call()
+    dt = time.perf_counter() - t0
+    h2d = N * 12 + (U + I) * (F + 1) * 4
+    d2h = (U + I) * (F + 1) * 4 + n_epochs * 8
+    return N * n_epochs / dt, dt, h2d, d2h, rm.tolist()
+
+
+def run_ours_single(args):
+    import torch
+    from matrix_factorization_b200 import engine
+    from matrix_factorization_b200._lib import lib
+
+    lib()
+    torch.cuda.set_device(0)
+    dev = torch.device("cuda", 0)
+    wl = gen_workload(args.workload, dev, uniform=args.uniform)
+    F, U, I, N = wl["F"], wl["U"], wl["I"], wl["N"]
+    g = torch.Generator(device=dev).manual_seed(5)
+    P = torch.randn(U, F, device=dev, generator=g) * 0.1
+    Q = torch.randn(I, F, device=dev, generator=g) * 0.1
+    bu, bi = torch.zeros(U, device=dev), torch.zeros(I, device=dev)
+    mu = float(wl["r"].double().mean().item())
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    plan = engine.Plan(wl["u"], wl["i"], wl["r"], U, I, n_factors=F, n_workers=args.workers, warps_per_cta=args.warps)
+    torch.cuda.synchronize()
+    plan_ms = 1e3 * (time.perf_counter() - t0)
+    info = plan.info()
+    sse = torch.zeros(args.warmup + args.steps, dtype=torch.float64, device=dev)
+
+    def step(k, ev=None):
+        if ev is not None:
+            ev[0].record()
+        engine.kmf_sgd_epoch(plan, "linear", P, Q, bu, bi, F, mu, wl["lr"], wl["reg"], 1.0 / F, 0.0, 5.0)
+        if ev is not None:
+            ev[1].record()
+        engine.kmf_sse_plan(plan, "linear", P, Q, bu, bi, F, mu, 1.0 / F, 0.0, 5.0, sse[k:k + 1])
+
+    for k in range(args.warmup):
+        step(k)
+    torch.cuda.synchronize()
+    clocks = ClockSampler(0)
+    clocks.start()
+    evs = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
+    start, end = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    start.record()
+    for k in range(args.steps):
+        step(args.warmup + k, evs[k])
+    end.record()
+    torch.cuda.synchronize()
+    clk = clocks.stop()
+    total_ms = start.elapsed_time(end)
+    sgd_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
+    rmse = [math.sqrt(v / N) for v in sse.cpu().numpy().tolist()]
+
+    peak, peak_src = load_peaks()
+    bytes_per_update = 16 * F + 28
+    achieved = bytes_per_update * N / (sgd_ms * 1e-3) / 1e9
+    e2e_v, e2e_dt, h2d, d2h, e2e_rmse = e2e_host_call(wl, wl["n_epochs"])
+    cpu_v, cpu_dt, cpu_n = cpu_baseline(wl, 2_000_000 if F <= 128 else 1_000_000)
+    line = {
+        "metric": "KernelMF SGD rating-updates/s", "value": N * args.steps / (total_ms * 1e-3),
+        "unit": "rating-updates/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": total_ms / args.steps, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": workload_name(args), "n_factors": F, "kernel": "linear", "lr": wl["lr"], "reg": wl["reg"],
+                   "step": "1 epoch = stratified SGD kernel + train-RMSE pass", "plan": info, "plan_build_ms": plan_ms,
+                   "l2": f"per-epoch working set {(N * 16 + (U + I) * F * 4) / 1e6:.0f} MB vs 126 MB L2, no explicit flush",
+                   "train_rmse_first_last": [rmse[0], rmse[-1]]},
+        "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
+                     "traffic": None, "kernel": "k_sgd_ring", "kernel_ms": sgd_ms, "bytes_per_update": bytes_per_update,
+                     "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
+        "cpu_baseline": {"value": cpu_v, "unit": "rating-updates/s", "cores": 1, "kind": "port",
+                         "sample": f"{cpu_n} ratings x 1 epoch of the same workload (shuffle + updates + RMSE), fp64, "
+                                   f"1 thread of {os.cpu_count()}"},
+        "e2e": {"value": e2e_v, "unit": "rating-updates/s", "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                "call": f"mfk_kmf_sgd_host: pinned host buffers, plan build, {wl['n_epochs']} epochs + RMSE, copy back",
+                "seconds_per_call": e2e_dt, "train_rmse_last": e2e_rmse[-1]},
+        "gpu_launches": 3 * args.steps,
+        "clocks": clk,
+    }
+    print(json.dumps(line))
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="ml-20m", choices=list(WORKLOADS))
+    ap.add_argument("--uniform", action="store_true", help="uniform (skew-free) pairs instead of Zipf")
+    ap.add_argument("--workers", type=int, default=0)
+    ap.add_argument("--warps", type=int, default=0)
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 0)
+    if args.impl == "reference":
+        return run_reference_arm(args)
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1 or args.gpus > 1:
+        from matrix_factorization_b200 import dist_bench
+
+        return dist_bench.run(args)
+    return run_ours_single(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -1,0 +1,66 @@
+"""
+Device mirrors of the estimators' host arrays.
+
+The public attributes (user_features, item_features, user_biases, item_biases) stay float64
+numpy arrays like the reference's.  Uploading them on every predict()/recommend() call would
+dominate small requests, so the fp32 device copy made by the last fit/update/predict is kept
+here, keyed by the identity of the numpy array (weak reference: the mirror dies with the
+array, and is never pickled).  If user code mutates an attribute array IN PLACE it must call
+`invalidate(array)` (replacing the attribute with a new array needs nothing).
+"""
+from __future__ import annotations
+
+import weakref
+
+import numpy as np
+
+from . import engine
+
+_ROWS: dict[int, tuple] = {}
+_VECS: dict[int, tuple] = {}
+
+
+def _register(table, arr: np.ndarray, tensor):
+    key = id(arr)
+
+    def _drop(_ref, key=key, table=table):
+        table.pop(key, None)
+
+    table[key] = (weakref.ref(arr, _drop), tensor)
+
+
+def _lookup(table, arr: np.ndarray):
+    ent = table.get(id(arr))
+    if ent is not None and ent[0]() is arr:
+        return ent[1]
+    return None
+
+
+def rows(arr: np.ndarray):
+    """fp32 [n, ld] device mirror of a float [n, F] host array (uploaded on first use)."""
+    t = _lookup(_ROWS, arr)
+    if t is None or t.shape[0] != arr.shape[0] or t.shape[1] != engine.round_up4(arr.shape[1]):
+        t = engine.upload_rows(arr)
+        _register(_ROWS, arr, t)
+    return t
+
+
+def vec(arr: np.ndarray):
+    t = _lookup(_VECS, arr)
+    if t is None or t.shape[0] != arr.shape[0]:
+        t = engine.upload_vec(arr)
+        _register(_VECS, arr, t)
+    return t
+
+
+def set_rows(arr: np.ndarray, tensor):
+    _register(_ROWS, arr, tensor)
+
+
+def set_vec(arr: np.ndarray, tensor):
+    _register(_VECS, arr, tensor)
+
+
+def invalidate(arr: np.ndarray):
+    _ROWS.pop(id(arr), None)
+    _VECS.pop(id(arr), None)

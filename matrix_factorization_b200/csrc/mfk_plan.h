@@ -1,0 +1,31 @@
+// Internal layout of the opaque mfk_plan handle (see mfk_plan.cu for how it is built).
+#pragma once
+#include <stdint.h>
+
+namespace mfk {
+// sort key: [worker | step | slot]
+constexpr int kPlanWorkerShift = 40;
+constexpr int kPlanStepShift = 24;
+}  // namespace mfk
+
+struct mfk_plan {
+    int64_t n = 0;
+    int32_t n_users = 0, n_items = 0;
+    int32_t W = 0;  // worker warps == user stripes == steps
+    int32_t n_ctas = 0, warps_per_cta = 0;
+    int32_t max_slots = 0;  // items per worker (rows of witems)
+    int64_t max_worker_ratings = 0, max_item_degree = 0, max_user_degree = 0;
+    // ratings sorted by (worker, step, slot); all device arrays of length n
+    int32_t *su = nullptr;     // user id
+    int32_t *si = nullptr;     // item id
+    int32_t *sslot = nullptr;  // item's slot inside its worker (index into the worker's smem stripe)
+    float *sr = nullptr;       // rating
+    int32_t *sstep = nullptr;  // step
+    int32_t *sidx = nullptr;   // index into the arrays given to mfk_plan_create
+    int64_t *wbeg = nullptr;   // [W+1] list bounds per worker
+    int32_t *witems = nullptr; // [max_slots][W] item id owned by (slot, worker) or -1
+    int32_t *iworker = nullptr, *islot = nullptr;  // per item
+    int32_t *ustripe = nullptr;                    // per user
+    int32_t *flags = nullptr;  // [W] ring progress flags (monotone across epochs)
+    int64_t epoch = 0;         // epochs run so far (flag base = epoch * (W + 1))
+};

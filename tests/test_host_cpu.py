@@ -1,0 +1,150 @@
+"""CPU: host-side logic of the drop-in API and the C-ABI surface (no compute calls)."""
+import json
+import os
+import pickle
+import re
+
+import numpy as np
+import pandas as pd
+import pytest
+
+import matrix_factorization_b200 as mfb
+from matrix_factorization_b200 import _lib
+from matrix_factorization_b200.data import synth_ratings, split_rows, SHAPES
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_cabi_exports_every_declared_symbol():
+    """Every function declared in include/mfk.h is exported by the built .so and bound in _lib."""
+    hdr = open(os.path.join(ROOT, "include", "mfk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    declared = set(re.findall(r"\b(mfk_[a-z0-9_]+)\s*\(", hdr))
+    assert len(declared) >= 20
+    L = _lib.lib()
+    for name in declared:
+        assert hasattr(L, name), f"{name} declared in mfk.h but not exported"
+    assert declared == set(_lib.SIGNATURES), declared ^ set(_lib.SIGNATURES)
+    assert L.mfk_abi_version() == 1
+
+
+def test_constructor_defaults_and_errors():
+    m = mfb.KernelMF()
+    assert (m.n_factors, m.n_epochs, m.kernel, m.reg, m.lr, m.init_mean, m.init_sd) == (100, 100, "linear", 1, 0.01, 0, 0.1)
+    assert m.gamma == 0.01 and m.min_rating == 0 and m.max_rating == 5 and m.verbose == 1
+    assert mfb.KernelMF(n_factors=50).gamma == 1 / 50
+    b = mfb.BaselineModel()
+    assert (b.method, b.n_epochs, b.reg, b.lr, b.verbose) == ("sgd", 100, 1, 0.01, 1)
+    with pytest.raises(ValueError, match="Kernel must be one of linear, sigmoid, or rbf"):
+        mfb.KernelMF(kernel="poly")
+    with pytest.raises(ValueError, match='Method param must be either "sgd" or "als"'):
+        mfb.BaselineModel(method="x")
+
+
+def test_sklearn_contract():
+    from sklearn.base import clone
+
+    m = mfb.KernelMF(n_factors=50, kernel="rbf", reg=0.1)
+    c = clone(m)
+    assert c.get_params() == m.get_params() and c.gamma == 0.02
+    c.set_params(n_factors=10)
+    assert c.gamma == 0.02  # resolved at construction, like the reference
+    assert pickle.loads(pickle.dumps(m)).get_params() == m.get_params()
+    assert set(mfb.__all__) == {"BaselineModel", "KernelMF", "RecommenderBase", "train_update_test_split"}
+
+
+def test_preprocess_matches_reference_bit_exact(golden_dir):
+    g = np.load(os.path.join(golden_dir, "preprocess.npz"))
+    m = mfb.BaselineModel(method="als", verbose=0)
+    train = pd.DataFrame({"user_id": g["train_user"], "item_id": g["train_item"]})
+    np.random.seed(int(g["fit_seed"]))
+    Xf = m._preprocess_data(train, pd.Series(g["train_rating"]), type="fit")
+    assert np.array_equal(Xf["user_id"].to_numpy(), g["fit_u"])
+    assert np.array_equal(Xf["item_id"].to_numpy(), g["fit_i"])
+    assert np.array_equal(Xf["rating"].to_numpy(), g["fit_r"])
+    assert list(m.user_id_map.keys()) == g["umap_keys"].tolist()
+    assert list(m.item_id_map.keys()) == g["imap_keys"].tolist()
+    assert list(m.user_id_map.values()) == list(range(m.n_users))
+    # same RNG consumption as the reference: the next draw must agree with a replay
+    nxt = np.random.random()
+    np.random.seed(int(g["fit_seed"]))
+    np.random.choice(len(train), size=len(train), replace=False)
+    assert nxt == np.random.random()
+
+    upd = pd.DataFrame({"user_id": g["upd_user"], "item_id": g["upd_item"]})
+    np.random.seed(int(g["upd_seed"]))
+    Xu, known, new = m._preprocess_data(upd, pd.Series(g["upd_rating"]), type="update")
+    assert np.array_equal(Xu["user_id"].to_numpy(), g["upd_u"])
+    assert np.array_equal(Xu["item_id"].to_numpy(), g["upd_i"])
+    assert np.array_equal(Xu["rating"].to_numpy(), g["upd_r"])
+    assert known == g["upd_known"].tolist() and new == g["upd_new"].tolist()
+    assert list(m.user_id_map.keys()) == g["umap_keys_after"].tolist()
+    assert m.n_users == len(g["umap_keys"])  # quirk: n_users is NOT bumped by update
+
+    pq = pd.DataFrame({"user_id": g["pq_user"], "item_id": g["pq_item"]})
+    Xp = m._preprocess_data(pq, type="predict")
+    assert np.array_equal(Xp["user_id"].to_numpy(), g["pq_u"]) and np.array_equal(Xp["item_id"].to_numpy(), g["pq_i"])
+
+
+def test_preprocess_edge_cases():
+    m = mfb.BaselineModel(verbose=0)
+    X = pd.DataFrame({"user_id": [1, 1, 2], "item_id": [7, 7, 8]})
+    with pytest.raises(ValueError, match="Duplicate user-item ratings in matrix"):
+        m._preprocess_data(X, pd.Series([1.0, 2.0, 3.0]), type="fit")
+    # string ids (the reference itself raises under pandas 3; semantics = first appearance on shuffled rows)
+    Xs = pd.DataFrame({"user_id": ["a", "b", "a", "c"], "item_id": ["x", "x", "y", "z"]})
+    np.random.seed(3)
+    out = m._preprocess_data(Xs, pd.Series([1.0, 2.0, 3.0, 4.0]), type="fit")
+    np.random.seed(3)
+    perm = np.random.choice(4, size=4, replace=False)
+    assert list(m.user_id_map.keys()) == list(dict.fromkeys(Xs.user_id.to_numpy()[perm]))
+    assert list(m.item_id_map.keys()) == list(dict.fromkeys(Xs.item_id.to_numpy()[perm]))
+    assert out["rating"].tolist() == [[1.0, 2.0, 3.0, 4.0][j] for j in perm]
+    # index-aligned rating assignment (recommender_base.py:123)
+    Xi = pd.DataFrame({"user_id": [1, 2, 3], "item_id": [4, 5, 6]}, index=[10, 11, 12])
+    y = pd.Series([3.0, 2.0, 1.0], index=[12, 11, 10])
+    np.random.seed(0)
+    o = m._preprocess_data(Xi, y, type="fit")
+    raw_u = {v: k for k, v in m.user_id_map.items()}
+    got = {raw_u[u]: r for u, r in zip(o["user_id"], o["rating"])}
+    assert got == {1: 1.0, 2: 2.0, 3: 3.0}
+    # known_users / contains_*
+    assert m.known_users == {1, 2, 3} and m.contains_item(5) and not m.contains_user(99)
+    # empty predict never touches the device
+    assert mfb.KernelMF(verbose=0).predict(pd.DataFrame({"user_id": [], "item_id": []})) == []
+
+
+def test_no_cpu_fallback_without_gpu():
+    import torch
+
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    df = synth_ratings(20, 15, 100, seed=1)
+    with pytest.raises(RuntimeError, match="CUDA"):
+        mfb.KernelMF(n_factors=4, n_epochs=1, verbose=0).fit(df[["user_id", "item_id"]], df["rating"])
+
+
+def test_train_update_test_split():
+    df = synth_ratings(60, 40, 1500, seed=5, min_per_user=6)
+    np.random.seed(1)
+    Xi, yi, Xu, yu, Xt, yt = mfb.train_update_test_split(df, frac_new_users=0.25)
+    held = set(Xu.user_id) | set(Xt.user_id)
+    assert len(held) == round(0.25 * df.user_id.nunique())
+    assert not (set(Xi.user_id) & held)
+    assert len(Xi) + len(Xu) + len(Xt) == len(df)
+    assert set(Xu.user_id) == set(Xt.user_id)
+    assert abs(len(Xu) - len(Xt)) <= len(held)
+    assert list(Xi.columns) == ["user_id", "item_id"] and yi.name == "rating"
+
+
+def test_synthetic_generator_shapes():
+    df = synth_ratings(200, 150, 5000, seed=9, min_per_user=5)
+    assert len(df) == 5000 and not df.duplicated(["user_id", "item_id"]).any()
+    assert df.user_id.nunique() <= 200 and df.groupby("user_id").size().min() >= 5
+    assert set(np.unique(df.rating)) <= {1.0, 2.0, 3.0, 4.0, 5.0}
+    # item popularity is skewed (Zipf ~ 1): the top item is far above the median item
+    cnt = df.groupby("item_id").size().sort_values(ascending=False)
+    assert cnt.iloc[0] > 5 * cnt.median()
+    tr, te = split_rows(df, 0.1, seed=0)
+    assert len(tr) + len(te) == len(df)
+    assert SHAPES["netflix"][0] == 480_189
