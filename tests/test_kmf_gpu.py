@@ -171,12 +171,12 @@ def test_edge_cases():
     P, Q, bu, bi = np.zeros((3, 8)) + 0.1, np.zeros((2, 8)) + 0.1, np.zeros(3), np.zeros(2)
     # empty rating set: nothing changes, no crash
     out = kmf._sgd(np.zeros((0, 3)), 3.0, bu, bi, P, Q, 2, "linear", 0.1, 0.01, 0.02, 0, 5, 0)
-    assert len(out[4]) == 2 and np.all(P == 0.1)
+    assert len(out[4]) == 2 and np.all(P == np.float64(np.float32(0.1)))  # device storage is fp32
     assert kmf._predict(np.zeros((0, 2)), 3.0, bu, bi, P, Q, 0, 5, "linear", 0.1, True) == ([], [])
     # a single user with every item (maximally ragged): one worker chain
     X = np.array([[0, 0, 4.0], [0, 1, 2.0]])
     kmf._sgd(X, 3.0, bu, bi, P, Q, 1, "linear", 0.1, 0.01, 0.02, 0, 5, 0)
-    assert np.all(P[1:] == 0.1) and not np.all(P[0] == 0.1)
+    assert np.all(P[1:] == np.float64(np.float32(0.1))) and not np.any(P[0] == np.float64(np.float32(0.1)))
     with pytest.raises(ValueError):
         kmf._sgd(X, 3.0, bu, bi, P, Q, 1, "poly", 0.1, 0.01, 0.02, 0, 5, 0)
     # ids out of range are rejected by the C ABI, not silently clipped
