@@ -236,6 +236,12 @@ def run_ours_single(args):
     end.record()
     torch.cuda.synchronize()
     clk = clocks.stop()
+    st = plan.stats()
+    hot = int(np.argmax(st[:, 0]))
+    ring_stats = {"max_worker_cycles": int(st[hot, 0]), "hot_worker": hot, "hot_blocked_cycles": int(st[hot, 1]),
+                  "hot_quads": int(st[hot, 2]), "hot_singles": int(st[hot, 3]),
+                  "median_worker_cycles": int(np.median(st[:, 0])), "median_blocked_cycles": int(np.median(st[:, 1])),
+                  "quads_total": int(st[:, 2].sum()), "singles_total": int(st[:, 3].sum())}
     total_ms = start.elapsed_time(end)
     sgd_ms = float(np.mean([a.elapsed_time(b) for a, b in evs]))
     rmse = [math.sqrt(v / N) for v in sse.cpu().numpy().tolist()]
@@ -243,8 +249,12 @@ def run_ours_single(args):
     peak, peak_src = load_peaks()
     bytes_per_update = 16 * F + 28
     achieved = bytes_per_update * N / (sgd_ms * 1e-3) / 1e9
-    e2e_v, e2e_dt, h2d, d2h, e2e_rmse = e2e_host_call(wl, wl["n_epochs"])
-    cpu_v, cpu_dt, cpu_n = cpu_baseline(wl, 2_000_000 if F <= 128 else 1_000_000)
+    if args.kernel_only:  # profiling runs (ncu): skip the host-call and CPU legs
+        e2e_v, e2e_dt, h2d, d2h, e2e_rmse = float("nan"), float("nan"), 0, 0, [float("nan")]
+        cpu_v, cpu_dt, cpu_n = float("nan"), 0.0, 0
+    else:
+        e2e_v, e2e_dt, h2d, d2h, e2e_rmse = e2e_host_call(wl, wl["n_epochs"])
+        cpu_v, cpu_dt, cpu_n = cpu_baseline(wl, 2_000_000 if F <= 128 else 1_000_000)
     line = {
         "metric": "KernelMF SGD rating-updates/s", "value": N * args.steps / (total_ms * 1e-3),
         "unit": "rating-updates/s", "n_gpus": 1, "steps": args.steps, "warmup": args.warmup,
@@ -256,7 +266,7 @@ def run_ours_single(args):
                    "train_rmse_first_last": [rmse[0], rmse[-1]]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": None, "kernel": "k_sgd_ring", "kernel_ms": sgd_ms, "bytes_per_update": bytes_per_update,
-                     "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0},
+                     "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "ring_stats": ring_stats},
         "cpu_baseline": {"value": cpu_v, "unit": "rating-updates/s", "cores": 1, "kind": "port",
                          "sample": f"{cpu_n} ratings x 1 epoch of the same workload (shuffle + updates + RMSE), fp64, "
                                    f"1 thread of {os.cpu_count()}"},
@@ -279,6 +289,7 @@ def main():
     ap.add_argument("--uniform", action="store_true", help="uniform (skew-free) pairs instead of Zipf")
     ap.add_argument("--workers", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
+    ap.add_argument("--kernel-only", action="store_true", help="skip the e2e host call and the CPU baseline (profiling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
     if args.impl == "reference":

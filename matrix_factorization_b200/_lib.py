@@ -49,6 +49,7 @@ SIGNATURES = {
     "mfk_plan_get_info": (_int, [_p, C.POINTER(PlanInfo)]),
     "mfk_plan_order": (_int, [_p, _p, _p]),
     "mfk_plan_assignment": (_int, [_p, _p, _p, _p]),
+    "mfk_plan_stats": (_int, [_p, _p, _p]),
     "mfk_kmf_sgd_epoch": (_int, [_p, _int, _p, _p, _p, _p, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _int,
                                  _int, _p]),
     "mfk_sse_workspace_bytes": (C.c_size_t, []),

@@ -59,7 +59,8 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         sp = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), headers_t):
             return obj, ""
-        cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", sp, "-o", obj]
+        extra = ["-DMFK_RING_PROFILE=1"] if os.environ.get("MFK_RING_PROFILE") == "1" else []
+        cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", sp, "-o", obj]
         if verbose:
             print(" ".join(cmd), flush=True)
         r = subprocess.run(cmd, capture_output=True, text=True)

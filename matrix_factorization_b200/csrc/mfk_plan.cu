@@ -82,14 +82,20 @@ __global__ void k_iota(int32_t *a, int32_t n) {
     if (k < n) a[k] = k;
 }
 
-// rank r (descending degree) -> snake-dealt bin and round
-__global__ void k_deal(const int32_t *__restrict__ sorted_ids, int32_t n_ids, int32_t W,
-                       int32_t *bin_of, int32_t *round_of, int32_t *table /* [rounds][W] or null */) {
+// rank r (descending degree) -> snake-dealt bin and round.  With n_ctas > 0 the snake position is
+// additionally spread CTA-major (position x -> warp x / n_ctas of CTA x % n_ctas): the heaviest
+// workers -- the epoch's critical path -- then sit on different SMs (and, as warps 0, 1, 2, ... of
+// their CTA, on different SM sub-partitions) instead of sharing the issue slots of one SM.
+__global__ void k_deal(const int32_t *__restrict__ sorted_ids, int32_t n_ids, int32_t W, int32_t n_ctas,
+                       int32_t warps_per_cta, int32_t *bin_of, int32_t *round_of,
+                       int32_t *table /* [rounds][W] or null */) {
     int32_t r = blockIdx.x * blockDim.x + threadIdx.x;
     if (r >= n_ids) return;
     int32_t id = sorted_ids[r];
     int32_t round = r / W, pos = r % W;
-    int32_t bin = (round & 1) ? (W - 1 - pos) : pos;
+    int32_t x = (round & 1) ? (W - 1 - pos) : pos;
+    // (+1: warp 0 of a CTA is the one that publishes through global memory -- keep the heaviest off it)
+    int32_t bin = n_ctas > 0 ? (x % n_ctas) * warps_per_cta + (x / n_ctas + 1) % warps_per_cta : x;
     bin_of[id] = bin;
     if (round_of) round_of[id] = round;
     if (table) table[(int64_t)round * W + bin] = id;
@@ -124,6 +130,41 @@ __global__ void k_gather(const uint64_t *__restrict__ keys, const int32_t *__res
         sr[k] = r[j];
         sslot[k] = (int32_t)(key & ((1ull << kPlanStepShift) - 1));
         sstep[k] = (int32_t)((key >> kPlanStepShift) & ((1ull << (kPlanWorkerShift - kPlanStepShift)) - 1));
+    }
+}
+
+// Schedule records streamed by the SGD kernel: {user, slot, rating bits, ctrl} with
+//   kCtrlDup     user occurs among the previous 15 records (the kernel prefetches user rows up to 8
+//                ratings ahead and must not prefetch a row it is about to rewrite), or belongs to the
+//                last partial 16-byte chunk of the bias array: such rows are read directly;
+//   kCtrlQuad    records k..k+3 have the same (worker, step, slot) key and none of them is a dup, so
+//                the four users are distinct and the kernel may resolve them as one exact 4-chain;
+//   kCtrlNewStep / kCtrlNewItem   block and item boundaries inside a worker's list.
+__global__ void k_build_records(const uint64_t *__restrict__ keys, const int32_t *__restrict__ su,
+                                const float *__restrict__ sr, int64_t n, int32_t n_users, int4 *rec) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    const uint64_t slot_mask = (1ull << kPlanStepShift) - 1;
+    for (; k < n; k += stride) {
+        const uint64_t key = keys[k];
+        auto is_dup = [&](int64_t x) {
+            int32_t u = su[x];
+            // users of the last partial 16-byte bias chunk are read directly too (no over-read of bu)
+            bool d = (u | 3) >= n_users;
+            for (int j = 1; j <= 15 && x - j >= 0; ++j) d |= (su[x - j] == u);
+            return d;
+        };
+        int32_t ctrl = (int32_t)((key >> kPlanStepShift) & 0xffff);
+        const bool dup = is_dup(k);
+        if (dup) ctrl |= kCtrlDup;
+        if (k == 0 || (keys[k - 1] >> kPlanStepShift) != (key >> kPlanStepShift)) ctrl |= kCtrlNewStep;
+        if (k == 0 || (keys[k - 1] >> kPlanWorkerShift) != (key >> kPlanWorkerShift) ||
+            (keys[k - 1] & slot_mask) != (key & slot_mask))
+            ctrl |= kCtrlNewItem;
+        if (!dup && k + 3 < n && keys[k + 1] == key && keys[k + 2] == key && keys[k + 3] == key &&
+            !is_dup(k + 1) && !is_dup(k + 2) && !is_dup(k + 3))
+            ctrl |= kCtrlQuad;
+        rec[k] = make_int4(su[k], (int32_t)(key & slot_mask), __float_as_int(sr[k]), ctrl);
     }
 }
 
@@ -214,17 +255,16 @@ void choose_workers(int64_t n, int32_t n_users, int32_t n_items, int sm_count, c
         // ~3 ratings per (worker, step) block keeps the ring hand-off amortised while all SMs
         // get work:  W ~ sqrt(n / 3), bounded by one full wave of 32-warp CTAs.
         double w = std::sqrt((double)std::max<int64_t>(n, 1) / 3.0);
-        W = (int32_t)std::max(1.0, std::min(w, (double)sm_count * 32));
+        W = (int32_t)std::max(1.0, std::min(w, (double)sm_count * 16));
         W = std::min(W, std::max(1, cap / 2));
     }
     int32_t k = req_k > 0 ? req_k : 0;
     if (k == 0) {
-        if (W >= sm_count * 4) k = std::min(32, std::max(4, (W + sm_count - 1) / sm_count));
+        if (W >= sm_count * 4) k = std::min(16, std::max(4, (W + sm_count - 1) / sm_count));
         else k = std::min(8, W);
     }
-    int32_t kmax = 32;
+    int32_t kmax = 16;  // 512-thread CTAs leave 128 registers per thread for the 4-chain path
     if (opts && opts->n_factors > 512) kmax = 8;
-    else if (opts && opts->n_factors > 256) kmax = 16;
     k = std::max(1, std::min(kmax, k));
     int32_t ctas = std::max(1, (W + k - 1) / k);
     if (req_w == 0 && ctas > sm_count) ctas = sm_count;
@@ -253,8 +293,8 @@ extern "C" int mfk_device_query(int device, int *sm_count, int *cc, size_t *smem
 
 static void plan_free(mfk_plan *p) {
     if (!p) return;
-    void *ptrs[] = {p->su, p->si, p->sslot, p->sr, p->sstep, p->sidx, p->wbeg, p->witems,
-                    p->iworker, p->islot, p->ustripe, p->flags};
+    void *ptrs[] = {p->su, p->si, p->sslot, p->sr, p->sstep, p->rec, p->sidx, p->wbeg, p->witems,
+                    p->iworker, p->islot, p->ustripe, p->flags, p->stats};
     for (void *q : ptrs)
         if (q) cudaFree(q);
     delete p;
@@ -316,6 +356,7 @@ extern "C" int mfk_plan_create(mfk_plan **out, const int32_t *d_u, const int32_t
     PLAN_CUDA(dalloc((void **)&p->sslot, nn * 4));
     PLAN_CUDA(dalloc((void **)&p->sr, nn * 4));
     PLAN_CUDA(dalloc((void **)&p->sstep, nn * 4));
+    PLAN_CUDA(dalloc((void **)&p->rec, nn * 16));
     PLAN_CUDA(dalloc((void **)&p->sidx, nn * 4));
     PLAN_CUDA(dalloc((void **)&p->wbeg, sizeof(int64_t) * (size_t)(W + 1)));
     PLAN_CUDA(dalloc((void **)&p->witems, sizeof(int32_t) * (size_t)p->max_slots * W));
@@ -324,6 +365,8 @@ extern "C" int mfk_plan_create(mfk_plan **out, const int32_t *d_u, const int32_t
     PLAN_CUDA(dalloc((void **)&p->ustripe, sizeof(int32_t) * (size_t)n_users));
     PLAN_CUDA(dalloc((void **)&p->flags, sizeof(int32_t) * (size_t)(W + 32)));
     PLAN_CUDA(cudaMemsetAsync(p->flags, 0, sizeof(int32_t) * (size_t)(W + 32), st));
+    PLAN_CUDA(dalloc((void **)&p->stats, sizeof(long long) * 12 * (size_t)W));
+    PLAN_CUDA(cudaMemsetAsync(p->stats, 0, sizeof(long long) * 12 * (size_t)W, st));
     PLAN_CUDA(cudaMemsetAsync(p->witems, 0xff, sizeof(int32_t) * (size_t)p->max_slots * W, st));
 
     int32_t *deg_u = nullptr, *deg_i = nullptr, *sorted_u = nullptr, *sorted_i = nullptr, *bad = nullptr;
@@ -355,9 +398,10 @@ extern "C" int mfk_plan_create(mfk_plan **out, const int32_t *d_u, const int32_t
         for (void *q : scratch) cudaFree(q);
         return rc;
     }
-    k_deal<<<(n_users + 255) / 256, 256, 0, st>>>(sorted_u, n_users, W, p->ustripe, nullptr, nullptr);
+    k_deal<<<(n_users + 255) / 256, 256, 0, st>>>(sorted_u, n_users, W, 0, 0, p->ustripe, nullptr, nullptr);
     PLAN_CUDA(cudaGetLastError());
-    k_deal<<<(n_items + 255) / 256, 256, 0, st>>>(sorted_i, n_items, W, p->iworker, p->islot, p->witems);
+    k_deal<<<(n_items + 255) / 256, 256, 0, st>>>(sorted_i, n_items, W, p->n_ctas, p->warps_per_cta, p->iworker,
+                                                    p->islot, p->witems);
     PLAN_CUDA(cudaGetLastError());
     {   // degree extremes for the info struct
         int32_t top_u = 0, top_i = 0, hu = 0, hi = 0;
@@ -389,6 +433,8 @@ extern "C" int mfk_plan_create(mfk_plan **out, const int32_t *d_u, const int32_t
                                                   end_bit, st));
         k_gather<<<grid_for(n), 256, 0, st>>>(keys_b, p->sidx, n, d_u, d_i, d_r, p->su, p->si, p->sslot,
                                                p->sr, p->sstep);
+        PLAN_CUDA(cudaGetLastError());
+        k_build_records<<<grid_for(n), 256, 0, st>>>(keys_b, p->su, p->sr, n, n_users, p->rec);
         PLAN_CUDA(cudaGetLastError());
         k_worker_bounds<<<(W + 1 + 255) / 256, 256, 0, st>>>(keys_b, n, W, p->wbeg);
         PLAN_CUDA(cudaGetLastError());
@@ -455,6 +501,13 @@ extern "C" int mfk_plan_order(const mfk_plan *plan, int64_t *d_order, void *stre
     cudaFree(pos_in);
     cudaFree(pos_out);
     cudaFree(step_out);
+    return MFK_OK;
+}
+
+extern "C" int mfk_plan_stats(const mfk_plan *plan, int64_t *d_stats, void *stream) {
+    MFK_REQUIRE(plan && d_stats, "mfk_plan_stats: null argument");
+    MFK_CUDA(cudaMemcpyAsync(d_stats, plan->stats, sizeof(long long) * 12 * (size_t)plan->W, cudaMemcpyDeviceToDevice,
+                             as_stream(stream)));
     return MFK_OK;
 }
 

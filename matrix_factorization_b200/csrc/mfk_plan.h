@@ -1,11 +1,17 @@
 // Internal layout of the opaque mfk_plan handle (see mfk_plan.cu for how it is built).
 #pragma once
+#include <cuda_runtime.h>
 #include <stdint.h>
 
 namespace mfk {
 // sort key: [worker | step | slot]
 constexpr int kPlanWorkerShift = 40;
 constexpr int kPlanStepShift = 24;
+// ctrl word of a schedule record: step in the low 16 bits, then flags
+constexpr int32_t kCtrlDup = 1 << 30;      // this user occurs among the previous 15 records (do not prefetch its row)
+constexpr int32_t kCtrlQuad = 1 << 29;     // records k..k+3 share worker, step and item, none is kCtrlDup
+constexpr int32_t kCtrlNewStep = 1 << 28;  // first record of a (worker, step) block
+constexpr int32_t kCtrlNewItem = 1 << 27;  // item differs from the previous record of this worker
 }  // namespace mfk
 
 struct mfk_plan {
@@ -21,11 +27,13 @@ struct mfk_plan {
     int32_t *sslot = nullptr;  // item's slot inside its worker (index into the worker's smem stripe)
     float *sr = nullptr;       // rating
     int32_t *sstep = nullptr;  // step
+    int4 *rec = nullptr;       // {user, slot, rating bits, ctrl}: what the SGD kernel streams
     int32_t *sidx = nullptr;   // index into the arrays given to mfk_plan_create
     int64_t *wbeg = nullptr;   // [W+1] list bounds per worker
     int32_t *witems = nullptr; // [max_slots][W] item id owned by (slot, worker) or -1
     int32_t *iworker = nullptr, *islot = nullptr;  // per item
     int32_t *ustripe = nullptr;                    // per user
     int32_t *flags = nullptr;  // [W] ring progress flags (monotone across epochs)
+    long long *stats = nullptr;  // [W][4] per-worker counters of the last SGD epoch (diagnostics)
     int64_t epoch = 0;         // epochs run so far (flag base = epoch * (W + 1))
 };

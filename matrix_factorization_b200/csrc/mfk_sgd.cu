@@ -9,31 +9,58 @@
 // live in the warp's private slice of shared memory (loaded once, written back once) -- and
 // walks its rating list in step order.  At step s it owns user stripe (w + s) mod W; stripes
 // move around the ring w+1 -> w, so a worker may enter step s only when its neighbour w+1 has
-// finished every step < s.  Hand-off is a monotone progress flag: shared memory inside a
-// CTA, a release/relaxed global flag across CTAs.  User rows are read and written through
-// L2 (strong loads), one warp per rating, 128-bit coalesced accesses, shuffle-reduced dot
-// product, bias/factor/kernel-gradient updates fused in registers.  Consecutive ratings of
-// one item keep q in registers (the hot-item chain never leaves the SM).
+// finished every step < s.  Hand-off is a monotone progress flag: shared memory inside a CTA,
+// a release-store / relaxed-load global flag across CTAs.
+//
+// Per rating: one warp, 128-bit coalesced accesses, shuffle-reduced dot product, bias / factor
+// / kernel-gradient updates fused in registers.  User rows (and the 16-byte chunk holding the
+// user bias) are prefetched D ratings ahead with cp.async.cg (L2-coherent, no L1) into a
+// per-warp shared-memory ring, as far as the neighbour's progress has released them.
+//
+// Hot-item chains (consecutive ratings of one item) are the epoch's critical path: the item row
+// stays in registers, and for the linear kernel four chained ratings are resolved at once --
+// all ten dot products (p_j.q, p_j.p_l) are reduced together and the four errors follow by a
+// scalar forward substitution, which is algebraically the sequential update rule
+//     q_{j+1} = (1-lr*reg) q_j - lr*err_j p_j,   err_j = mu + b_u + b_i + p_j.q_j - r_j
+// (kernels.py:145-178) with one reduction latency per four ratings instead of four.
 #include <algorithm>
+#include <cstdlib>
 
 #include "mfk_common.cuh"
 #include "mfk_plan.h"
 
+#ifndef MFK_RING_PROFILE
+#define MFK_RING_PROFILE 0
+#endif
+#if MFK_RING_PROFILE
+#define PROF_T0() long long prof_t_ = clock64()
+#define PROF_ADD(slot) do { long long n_ = clock64(); prof[slot] += n_ - prof_t_; prof_t_ = n_; } while (0)
+#else
+#define PROF_T0() do { } while (0)
+#define PROF_ADD(slot) do { } while (0)
+#endif
+
 namespace mfk {
 
+constexpr int kRingDepthMax = 8;
+
 struct RingView {
-    const int32_t *su, *si, *sslot, *sstep;
-    const float *sr;
+    const int4 *rec;  // per rating {user, slot, rating bits, ctrl}; ctrl = step | kCtrl* flags
     const int64_t *wbeg;
     const int32_t *witems;
     int32_t *flags;
     int32_t W, k, max_slots;
+    int32_t depth;  // prefetch ring depth D (2..kRingDepthMax)
+    unsigned long long watchdog_ns;  // trap if a wait sees no progress for this long (0 = never)
+    long long *stats;                // [W][4]: total cycles, cycles blocked in hand-off waits, 4-chains, singles
+    long long *prof;                 // [W][8]: phase cycle counters (only written by MFK_RING_PROFILE builds)
 };
 
 struct SgdParams {
     float *P, *Q, *bu, *bi;
     int32_t F;   // n_factors rounded up to a multiple of 4 (columns that exist in memory)
     int32_t ld;  // row stride in floats
+    int32_t n_users;
     float mu, lr, reg, gamma, a, c;
     int32_t upd_user, upd_item;
     int32_t base;  // flag base of this epoch
@@ -44,9 +71,10 @@ struct Ring {
     volatile int32_t *sflags;  // shared, one per warp of the CTA
     int32_t *gpub;             // global flag this warp publishes (warp 0 only) or nullptr
     const int32_t *gpoll;      // global flag this warp polls (last warp only) or nullptr
-    int32_t warp, base, pub, rel;
-    uint32_t spins;
-    unsigned long long t0;
+    int32_t warp, base, pub, rel, pending;
+    int32_t last_rel;
+    unsigned long long t0, watchdog_ns;
+    long long wait_cycles;
     bool dirty;
 
     __device__ __forceinline__ void publish(int32_t t) {
@@ -58,43 +86,64 @@ struct Ring {
             sflags[warp] = base + t;
         }
     }
-    __device__ __forceinline__ int32_t poll() {
-        int32_t f = gpoll ? ld_strong_i(gpoll) : sflags[warp + 1];
-        f -= base;
-        // watchdog: a ring that makes no progress for ~4 s is a bug -- trap instead of hanging the GPU
-        if (((++spins) & 0xfffu) == 0) {
-            unsigned long long now;
-            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
-            if (f > rel || t0 == 0) t0 = now;
-            else if (now - t0 > 4000000000ull) __trap();
-        }
-        return f > rel ? f : rel;
+    __device__ __forceinline__ int32_t load_flag() const {
+        return (gpoll ? ld_strong_i(gpoll) : sflags[warp + 1]) - base;
     }
-    // Block until every step < s of the neighbour is complete; forwards progress meanwhile.
+    // Non-blocking look at the neighbour: consume the flag value requested last time, request a new
+    // one (the load's latency overlaps the rating being processed).
+    __device__ __forceinline__ void refresh_async() {
+        int32_t f = pending - base;
+        if (f > rel) rel = f;
+        pending = gpoll ? ld_strong_i(gpoll) : sflags[warp + 1];
+    }
+    // Wait until the neighbour has completed every step < target, forwarding (publishing, capped at
+    // `cap`) the progress observed meanwhile.  The wait loop is a handful of instructions and backs off with nanosleep so that
+    // waiting warps leave the issue slots to the working warps of their SM sub-partition.
+    __device__ __forceinline__ void wait_for(int32_t target, int32_t cap) {
+        long long c0 = clock64();
+        unsigned ns = 64, it = 0;
+        for (;;) {
+            int32_t f = load_flag();
+            if (f > rel) {
+                rel = f;
+                int32_t t = min(cap, rel + 1);
+                if (t > pub) publish(t);
+                if (rel >= target) break;
+                ns = 64;
+                continue;
+            }
+            __nanosleep(ns);
+            if (ns < 2048) ns <<= 1;
+            if (((++it) & 0x3ffu) == 0 && watchdog_ns) {  // a ring without progress for seconds is a bug: trap
+                unsigned long long now;
+                asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                if (t0 == 0 || rel != last_rel) { t0 = now; last_rel = rel; }
+                else if (now - t0 > watchdog_ns) __trap();
+            }
+        }
+        wait_cycles += clock64() - c0;
+    }
+    // Block until every step < s of the neighbour is complete.
     __device__ __forceinline__ void advance_to(int32_t s) {
         if (dirty) {
-            if (!gpub) __threadfence_block();  // release at CTA scope; gpu scope rides on st.release
+            if (!gpub) asm volatile("fence.acq_rel.cta;" ::: "memory");  // CTA-scope release; gpu scope rides on st.release
             dirty = false;
         }
-        for (;;) {
-            int32_t t = min(s, rel + 1);
-            if (t > pub) publish(t);
-            if (rel >= s) break;
-            rel = poll();
-        }
+        int32_t t = min(s, rel + 1);
+        if (t > pub) publish(t);
+        if (rel >= s) return;
+        wait_for(s, s);
     }
     // After the last rating: keep forwarding until the whole ring has drained (pub == W).
     __device__ __forceinline__ void finish(int32_t W) {
         if (dirty) {
-            if (!gpub) __threadfence_block();
+            if (!gpub) asm volatile("fence.acq_rel.cta;" ::: "memory");
             dirty = false;
         }
-        for (;;) {
-            int32_t t = min(W, rel + 1);
-            if (t > pub) publish(t);
-            if (pub >= W) break;
-            rel = poll();
-        }
+        int32_t t = min(W, rel + 1);
+        if (t > pub) publish(t);
+        if (pub >= W) return;
+        wait_for(W - 1, W);  // rel >= W-1  =>  pub == W
     }
 };
 
@@ -128,6 +177,25 @@ __device__ __forceinline__ void store_row(const Row<NV> &x, float *row, int lane
     }
 }
 
+__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
+    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+// wait until at most n of this thread's cp.async groups are pending (n is warp-uniform, 0..7)
+__device__ __forceinline__ void cp_async_wait_dyn(int n) {
+    switch (n) {
+        case 0: asm volatile("cp.async.wait_group 0;" ::: "memory"); break;
+        case 1: asm volatile("cp.async.wait_group 1;" ::: "memory"); break;
+        case 2: asm volatile("cp.async.wait_group 2;" ::: "memory"); break;
+        case 3: asm volatile("cp.async.wait_group 3;" ::: "memory"); break;
+        case 4: asm volatile("cp.async.wait_group 4;" ::: "memory"); break;
+        case 5: asm volatile("cp.async.wait_group 5;" ::: "memory"); break;
+        case 6: asm volatile("cp.async.wait_group 6;" ::: "memory"); break;
+        default: asm volatile("cp.async.wait_group 7;" ::: "memory"); break;
+    }
+}
+
 // One SGD step on registers.  p, q, ub, ib are updated in place (subject to the flags).
 template <int KERNEL, int NV>
 __device__ __forceinline__ void sgd_step(Row<NV> &p, Row<NV> &q, float &ub, float &ib, float r,
@@ -155,13 +223,12 @@ __device__ __forceinline__ void sgd_step(Row<NV> &p, Row<NV> &q, float &ub, floa
     acc = warp_sum(acc);
 
     const float lr = prm.lr, reg = prm.reg;
-    float gp, gq;  // p -= lr*(gp*q' + reg*p) with q' = q (linear/sigmoid) or (q - p) (rbf)
+    float gp;  // p -= lr*(gp*q' + reg*p) with q' = q (linear/sigmoid) or (q - p) (rbf)
     if (KERNEL == MFK_KERNEL_LINEAR) {
         float err = (prm.mu + ib + ub + acc) - r;  // kernels.py:145-153
         if (prm.upd_user) ub -= lr * (err + reg * ub);
         if (prm.upd_item) ib -= lr * (err + reg * ib);
         gp = err;
-        gq = err;
     } else if (KERNEL == MFK_KERNEL_SIGMOID) {
         float x = prm.mu + ub + ib + acc;  // kernels.py:224-234
         float ex = expf(-x);
@@ -171,13 +238,11 @@ __device__ __forceinline__ void sgd_step(Row<NV> &p, Row<NV> &q, float &ub, floa
         if (prm.upd_user) ub -= lr * (err * D + reg * ub);
         if (prm.upd_item) ib -= lr * (err * D + reg * ib);
         gp = err * D;
-        gq = err * D;
     } else {
         float E = expf(-prm.gamma * acc);  // kernels.py:301-309
         float err = (prm.a + prm.c * E) - r;
         float D = 2.0f * E * prm.gamma;  // no factor c
         gp = err * D;
-        gq = err * D;
     }
     const float decay = 1.0f - lr * reg;
 #pragma unroll
@@ -190,10 +255,10 @@ __device__ __forceinline__ void sgd_step(Row<NV> &p, Row<NV> &q, float &ub, floa
             pn.y = pv.y - lr * (gp * (qv.y - pv.y) + reg * pv.y);
             pn.z = pv.z - lr * (gp * (qv.z - pv.z) + reg * pv.z);
             pn.w = pv.w - lr * (gp * (qv.w - pv.w) + reg * pv.w);
-            qn.x = qv.x - lr * (gq * (pv.x - qv.x) + reg * qv.x);
-            qn.y = qv.y - lr * (gq * (pv.y - qv.y) + reg * qv.y);
-            qn.z = qv.z - lr * (gq * (pv.z - qv.z) + reg * qv.z);
-            qn.w = qv.w - lr * (gq * (pv.w - qv.w) + reg * qv.w);
+            qn.x = qv.x - lr * (gp * (pv.x - qv.x) + reg * qv.x);
+            qn.y = qv.y - lr * (gp * (pv.y - qv.y) + reg * qv.y);
+            qn.z = qv.z - lr * (gp * (pv.z - qv.z) + reg * qv.z);
+            qn.w = qv.w - lr * (gp * (pv.w - qv.w) + reg * qv.w);
         } else {
             // p -= lr*(g*q + reg*p) == decay*p - (lr*g)*q   (both sides use the OLD p, q)
             float lg = lr * gp;
@@ -211,40 +276,106 @@ __device__ __forceinline__ void sgd_step(Row<NV> &p, Row<NV> &q, float &ub, floa
     }
 }
 
+__device__ __forceinline__ float dot4(const float4 &a, const float4 &b, float acc) {
+    acc = fmaf(a.x, b.x, acc);
+    acc = fmaf(a.y, b.y, acc);
+    acc = fmaf(a.z, b.z, acc);
+    return fmaf(a.w, b.w, acc);
+}
+// x = ca*x - cb*y  (elementwise)
+__device__ __forceinline__ float4 axmby(float ca, const float4 &x, float cb, const float4 &y) {
+    float4 o;
+    o.x = fmaf(-cb, y.x, ca * x.x);
+    o.y = fmaf(-cb, y.y, ca * x.y);
+    o.z = fmaf(-cb, y.z, ca * x.z);
+    o.w = fmaf(-cb, y.w, ca * x.w);
+    return o;
+}
+
+// Sum each of ten per-lane partials over the warp and return all ten totals in every lane.
+// Recursive halving: at each butterfly stage a lane keeps one half of its values and sends the other
+// half to its partner, so 5+3+2+1+1 = 12 shuffles replace the 50 of ten separate butterflies; ten
+// independent index-shuffles then broadcast the totals (value i ends up in lane kQuadLane[i]).
+__device__ __forceinline__ void reduce10(float (&v)[10], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8, b2 = lane & 4, b1 = lane & 2;
+    float a[5], b[3], c[2];
+#pragma unroll
+    for (int i = 0; i < 5; ++i) {
+        float send = b4 ? v[i] : v[i + 5];
+        float keep = b4 ? v[i + 5] : v[i];
+        a[i] = keep + __shfl_xor_sync(0xffffffffu, send, 16);
+    }
+    {
+        float s0 = b3 ? a[0] : a[3], k0 = b3 ? a[3] : a[0];
+        float s1 = b3 ? a[1] : a[4], k1 = b3 ? a[4] : a[1];
+        float s2 = b3 ? a[2] : 0.f, k2 = b3 ? 0.f : a[2];
+        b[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 8);
+        b[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 8);
+        b[2] = k2 + __shfl_xor_sync(0xffffffffu, s2, 8);
+    }
+    {
+        float s0 = b2 ? b[0] : b[2], k0 = b2 ? b[2] : b[0];
+        float s1 = b2 ? b[1] : 0.f, k1 = b2 ? 0.f : b[1];
+        c[0] = k0 + __shfl_xor_sync(0xffffffffu, s0, 4);
+        c[1] = k1 + __shfl_xor_sync(0xffffffffu, s1, 4);
+    }
+    float d = (b1 ? c[1] : c[0]) + __shfl_xor_sync(0xffffffffu, b1 ? c[0] : c[1], 2);
+    d += __shfl_xor_sync(0xffffffffu, d, 1);
+    // value i: i<5 -> bit4 = 0, a-index i;  a-index 0,1,2 -> bit3 = 0 (b-index same), 3,4 -> bit3 = 1 (b 0,1);
+    // b-index 0,1 -> bit2 = 0 (c-index same), 2 -> bit2 = 1 (c 0);  c-index = bit1.
+    constexpr int kQuadLane[10] = {0, 2, 4, 8, 10, 16, 18, 20, 24, 26};
+#pragma unroll
+    for (int i = 0; i < 10; ++i) v[i] = __shfl_sync(0xffffffffu, d, kQuadLane[i]);
+}
+
 // NV = number of float4 per lane (row of up to 128*NV floats); NV == 0 is the bias-only model.
 template <int NV>
 constexpr int ring_max_threads() {
-    return NV >= 8 ? 256 : (NV >= 4 ? 512 : 1024);  // keeps the row registers out of local memory
+    return NV >= 8 ? 256 : 512;  // >= 128 registers per thread: the chain code must not spill or rematerialise
 }
 
 template <int KERNEL, int NV, bool QSMEM>
 __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView rv, SgdParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t *sflags = reinterpret_cast<int32_t *>(smem_raw);  // [32]
-    float *sq_all = reinterpret_cast<float *>(smem_raw + 128);
+    float *swarp_all = reinterpret_cast<float *>(smem_raw + 128);
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     const int32_t w = blockIdx.x * rv.k + warp;
     constexpr int NVR = NV > 0 ? NV : 1;
-    const bool has_bias = (KERNEL != MFK_KERNEL_RBF);
+    constexpr bool has_bias = (KERNEL != MFK_KERNEL_RBF);
+    constexpr bool kQuads = (KERNEL == MFK_KERNEL_LINEAR) && (NV == 1 || NV == 2);
+    constexpr uint32_t RS = 128u * NV + 4u;  // ring slot: a full-width row (zero beyond F) + the 16-byte bias chunk
+    const int D = rv.depth;                  // power of two, >= 2
+    const uint32_t dmask = (uint32_t)D - 1u;
+    const int ld = prm.ld, F = prm.F;
+    const int lc = 4 * lane;
 
     if (lane == 0) sflags[warp] = prm.base;
-    // per-warp slice of shared memory: max_slots rows of ld floats, then max_slots item biases
-    float *sq = nullptr, *sbi = nullptr;
+    // per-warp slice of shared memory:
+    //   [Q stripe: max_slots rows of ld floats + max_slots item biases]   (QSMEM only)
+    //   [prefetch ring: D slots of RS floats]   [record window: 64 x int4]
+    const size_t q_floats = QSMEM ? (((size_t)rv.max_slots * (size_t)(ld + 1) + 3) & ~(size_t)3) : 0;
+    const size_t per_warp = q_floats + (size_t)D * RS + 256;
+    float *sq = swarp_all + (size_t)warp * per_warp;
+    float *sbi = sq + (size_t)rv.max_slots * ld;
+    float *sring = sq + q_floats;
+    int4 *srec = reinterpret_cast<int4 *>(sring + (size_t)D * RS);
     if (QSMEM) {
-        size_t per_warp = (size_t)rv.max_slots * (size_t)(prm.ld + 1);
-        per_warp = (per_warp + 3) & ~(size_t)3;
-        sq = sq_all + (size_t)warp * per_warp;
-        sbi = sq + (size_t)rv.max_slots * prm.ld;
         for (int s = 0; s < rv.max_slots; ++s) {
             int32_t it = rv.witems[(int64_t)s * rv.W + w];
             if (it < 0) continue;
             if (NV > 0) {
                 Row<NVR> t;
-                load_row<NVR>(t, prm.Q + (size_t)it * prm.ld, lane, prm.F);
-                store_row<NVR>(t, sq + (size_t)s * prm.ld, lane, prm.F);
+                load_row<NVR>(t, prm.Q + (size_t)it * ld, lane, F);
+                store_row<NVR>(t, sq + (size_t)s * ld, lane, F);
             }
             if (lane == 0) sbi[s] = has_bias ? prm.bi[it] : 0.f;
         }
+    }
+    for (int d = 0; d < D; ++d) {  // zero the ring once: columns beyond F are never written again
+#pragma unroll
+        for (int v = 0; v < NV; ++v) *reinterpret_cast<float4 *>(sring + d * RS + lc + 128 * v) = make_float4(0.f, 0.f, 0.f, 0.f);
+        if (lane == 0) *reinterpret_cast<float4 *>(sring + d * RS + 128 * NV) = make_float4(0.f, 0.f, 0.f, 0.f);
     }
     __syncthreads();
 
@@ -254,91 +385,232 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
     ring.base = prm.base;
     ring.pub = 0;
     ring.rel = 0;
+    ring.pending = prm.base;
     ring.dirty = false;
-    ring.spins = 0;
+    ring.last_rel = -1;
     ring.t0 = 0;
+    ring.watchdog_ns = rv.watchdog_ns;
+    ring.wait_cycles = 0;
+    const long long clk_start = clock64();
+    int32_t n_quads = 0, n_singles = 0;
+#if MFK_RING_PROFILE
+    long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 0 step hand-off, 1 prefetch issue, 2 item switch, 3 cp wait,
+                                                  // 4 quad math, 5 quad update/store, 6 single, 7 window slide
+#endif
     ring.gpub = (warp == 0) ? rv.flags + w : nullptr;
     {
         int32_t nb = (w + 1 == rv.W) ? 0 : w + 1;
         ring.gpoll = (warp == rv.k - 1) ? rv.flags + nb : nullptr;
     }
 
-    const int64_t beg = rv.wbeg[w], end = rv.wbeg[w + 1];
-    int32_t cur_step = -1;
-    int32_t cur_item = -1;  // slot (QSMEM) or item id whose q / ib are live in registers
+    const int64_t beg = rv.wbeg[w];
+    const uint32_t n_list = (uint32_t)(rv.wbeg[w + 1] - beg);
+    const int4 *recs = rv.rec + beg;
+    int32_t cur_slot = -1, cur_item = -1;  // slot / item id whose q, ib are live in registers
     Row<NVR> q;
     float ib = 0.f;
 #pragma unroll
     for (int j = 0; j < NVR; ++j) q.v[j] = make_float4(0.f, 0.f, 0.f, 0.f);
 
     auto flush_q = [&]() {
-        if (cur_item < 0 || !prm.upd_item) return;
+        if (cur_slot < 0 || !prm.upd_item) return;
         if (QSMEM) {
-            if (NV > 0) store_row<NVR>(q, sq + (size_t)cur_item * prm.ld, lane, prm.F);
-            if (lane == 0) sbi[cur_item] = ib;
+            if (NV > 0) store_row<NVR>(q, sq + (size_t)cur_slot * ld, lane, F);
+            if (lane == 0) sbi[cur_slot] = ib;
         } else {
-            if (NV > 0) store_row<NVR>(q, prm.Q + (size_t)cur_item * prm.ld, lane, prm.F);
+            if (NV > 0) store_row<NVR>(q, prm.Q + (size_t)cur_item * ld, lane, F);
             if (has_bias && lane == 0) prm.bi[cur_item] = ib;
         }
     };
+    auto load_q = [&](int32_t slot) {
+        flush_q();
+        cur_slot = slot;
+        if (QSMEM) {
+            if (NV > 0) load_row<NVR>(q, sq + (size_t)slot * ld, lane, F);
+            ib = sbi[slot];
+        } else {
+            cur_item = rv.witems[(int64_t)slot * rv.W + w];
+            if (NV > 0) load_row<NVR>(q, prm.Q + (size_t)cur_item * ld, lane, F);
+            ib = has_bias ? prm.bi[cur_item] : 0.f;
+        }
+    };
 
-    Row<NVR> pn;  // prefetched / forwarded user row of the next rating
-    float ubn = 0.f;
-    bool have_next = false;
+    // ---- record window [w0, w0+64) in shared memory, the following batch staged in registers
+    const int4 rec_none = make_int4(0, 0, 0, 0xffff);
+    uint32_t w0 = 0;
+    srec[lane] = (lane < n_list) ? __ldcs(recs + lane) : rec_none;
+    srec[32 + lane] = (32u + lane < n_list) ? __ldcs(recs + 32 + lane) : rec_none;
+    int4 next_rec = (64u + lane < n_list) ? __ldcs(recs + 64 + lane) : rec_none;
+    __syncwarp();
 
-    for (int64_t b0 = beg; b0 < end; b0 += 32) {
-        const int64_t kk = b0 + lane;
-        const bool valid = kk < end;
-        const int32_t ru = valid ? ld_stream_i(rv.su + kk) : 0;
-        const int32_t ri = valid ? ld_stream_i((QSMEM ? rv.sslot : rv.si) + kk) : 0;
-        const float rr = valid ? ld_stream_f(rv.sr + kk) : 0.f;
-        const int32_t rs = valid ? ld_stream_i(rv.sstep + kk) : 0;
-        const int cnt = (int)min((int64_t)32, end - b0);
-        for (int j = 0; j < cnt; ++j) {
-            const int32_t u = __shfl_sync(0xffffffffu, ru, j);
-            const int32_t it = __shfl_sync(0xffffffffu, ri, j);
-            const float r = __shfl_sync(0xffffffffu, rr, j);
-            const int32_t s = __shfl_sync(0xffffffffu, rs, j);
-            if (s != cur_step) {
-                ring.advance_to(s);
-                cur_step = s;
+    // ---- prefetch ring: index x lives in slot x & (D-1); one cp.async group per index
+    uint32_t pf = 0;  // next index to issue
+    auto slot_of = [&](uint32_t x) { return sring + (x & dmask) * RS; };
+    auto issue_row = [&](uint32_t x, int32_t u, int32_t ctl) {  // the row only; closes the index's group
+        if (NV > 0 && !(ctl & kCtrlDup)) {
+            float *slot = slot_of(x);
+            const float *row = prm.P + (size_t)u * ld;
+#pragma unroll
+            for (int j = 0; j < NVR; ++j) {
+                int c = lc + 128 * j;
+                if (c < F) cp_async16(slot + c, row + c);
             }
-            // ---- operands
+        }
+        cp_async_commit();
+    };
+    auto issue = [&](uint32_t x, int32_t u, int32_t ctl) {
+        if (has_bias && lane == 0 && !(ctl & kCtrlDup)) cp_async16(slot_of(x) + 128 * NV, prm.bu + (u & ~3));
+        issue_row(x, u, ctl);
+    };
+
+    // constants of the update rule
+    const float aq = prm.upd_item ? 1.0f - prm.lr * prm.reg : 1.0f, lq = prm.upd_item ? prm.lr : 0.f;
+    const float ap = prm.upd_user ? 1.0f - prm.lr * prm.reg : 1.0f, lp = prm.upd_user ? prm.lr : 0.f;
+    const float aq2 = aq * aq, aq3 = aq2 * aq;
+
+    uint32_t k = 0;
+    bool first = true;
+    while (k < n_list) {
+        PROF_T0();
+        const int4 rc = srec[k & 63u];
+        const int32_t ctrl = rc.w;
+        if (first || (ctrl & kCtrlNewStep)) ring.advance_to(ctrl & 0xffff);
+        PROF_ADD(0);
+        // issue as far as the ring depth, the record window and the neighbour's progress allow
+        {
+            const uint32_t lim = min(min(n_list, k + (uint32_t)D), w0 + 64u);
+            if (pf + 4u <= lim) {  // common case in a chain: four at once, one progress check
+                const int4 a0 = srec[pf & 63u], a1 = srec[(pf + 1u) & 63u], a2 = srec[(pf + 2u) & 63u],
+                           a3 = srec[(pf + 3u) & 63u];
+                if ((a3.w & 0xffff) <= ring.rel) {
+                    if (has_bias && lane < 4) {  // the four bias chunks with one instruction (lane j -> index pf+j)
+                        const int32_t uj = lane == 0 ? a0.x : (lane == 1 ? a1.x : (lane == 2 ? a2.x : a3.x));
+                        const int32_t cj = lane == 0 ? a0.w : (lane == 1 ? a1.w : (lane == 2 ? a2.w : a3.w));
+                        if (!(cj & kCtrlDup)) cp_async16(slot_of(pf + (uint32_t)lane) + 128 * NV, prm.bu + (uj & ~3));
+                    }
+                    issue_row(pf, a0.x, a0.w);
+                    issue_row(pf + 1u, a1.x, a1.w);
+                    issue_row(pf + 2u, a2.x, a2.w);
+                    issue_row(pf + 3u, a3.x, a3.w);
+                    pf += 4u;
+                }
+            }
+            while (pf < lim) {
+                const int4 rp = srec[pf & 63u];
+                if ((rp.w & 0xffff) > ring.rel) {
+                    ring.refresh_async();  // non-blocking look at the neighbour; otherwise retry next rating
+                    if ((rp.w & 0xffff) > ring.rel) break;
+                }
+                issue(pf, rp.x, rp.w);
+                ++pf;
+            }
+        }
+        PROF_ADD(1);
+        if (first || (ctrl & kCtrlNewItem)) load_q(rc.y);
+        first = false;
+        PROF_ADD(2);
+        const int32_t u = rc.x;
+
+        if (kQuads && (ctrl & kCtrlQuad) && pf >= k + 4u) {
+            // ---- exact 4-chain: same item, same step, four distinct users, all four rows in flight
+            const int4 r1 = srec[(k + 1u) & 63u], r2 = srec[(k + 2u) & 63u], r3 = srec[(k + 3u) & 63u];
+            cp_async_wait_dyn((int)(pf - 4u - k));
+            __syncwarp();  // lane 0's bias-chunk copies become visible to every lane
+            PROF_ADD(3);
+            const float *s0 = slot_of(k), *s1 = slot_of(k + 1u), *s2 = slot_of(k + 2u), *s3 = slot_of(k + 3u);
+            Row<NVR> p0, p1, p2, p3;
+#pragma unroll
+            for (int v = 0; v < NVR; ++v) {
+                p0.v[v] = *reinterpret_cast<const float4 *>(s0 + lc + 128 * v);
+                p1.v[v] = *reinterpret_cast<const float4 *>(s1 + lc + 128 * v);
+                p2.v[v] = *reinterpret_cast<const float4 *>(s2 + lc + 128 * v);
+                p3.v[v] = *reinterpret_cast<const float4 *>(s3 + lc + 128 * v);
+            }
+            const float ub0 = s0[128 * NV + (u & 3)], ub1 = s1[128 * NV + (r1.x & 3)];
+            const float ub2 = s2[128 * NV + (r2.x & 3)], ub3 = s3[128 * NV + (r3.x & 3)];
+            // ten reductions at once: t_j = p_j.q (0..3), g_jl = p_j.p_l for l < j (10,20,21,30,31,32)
+            float v10[10];
+#pragma unroll
+            for (int i = 0; i < 10; ++i) v10[i] = 0.f;
+#pragma unroll
+            for (int v = 0; v < NVR; ++v) {
+                const float4 qv = q.v[v];
+                v10[0] = dot4(p0.v[v], qv, v10[0]);
+                v10[1] = dot4(p1.v[v], qv, v10[1]);
+                v10[2] = dot4(p2.v[v], qv, v10[2]);
+                v10[3] = dot4(p3.v[v], qv, v10[3]);
+                v10[4] = dot4(p1.v[v], p0.v[v], v10[4]);
+                v10[5] = dot4(p2.v[v], p0.v[v], v10[5]);
+                v10[6] = dot4(p2.v[v], p1.v[v], v10[6]);
+                v10[7] = dot4(p3.v[v], p0.v[v], v10[7]);
+                v10[8] = dot4(p3.v[v], p1.v[v], v10[8]);
+                v10[9] = dot4(p3.v[v], p2.v[v], v10[9]);
+            }
+            reduce10(v10, lane);
+            // forward substitution (item bias rides along as an extra all-ones factor)
+            const float e0 = (prm.mu + ub0 - __int_as_float(rc.z)) + (v10[0] + ib);
+            const float e1 = (prm.mu + ub1 - __int_as_float(r1.z)) + aq * (v10[1] + ib) - lq * (e0 * (v10[4] + 1.f));
+            const float e2 = (prm.mu + ub2 - __int_as_float(r2.z)) + aq2 * (v10[2] + ib) -
+                             lq * (aq * e0 * (v10[5] + 1.f) + e1 * (v10[6] + 1.f));
+            const float e3 = (prm.mu + ub3 - __int_as_float(r3.z)) + aq3 * (v10[3] + ib) -
+                             lq * (aq2 * e0 * (v10[7] + 1.f) + aq * e1 * (v10[8] + 1.f) + e2 * (v10[9] + 1.f));
+            PROF_ADD(4);
+            // sequential update with the errors known:  p_j' uses q_j,  q_{j+1} uses the OLD p_j
+            float *g0 = prm.P + (size_t)u * ld, *g1 = prm.P + (size_t)r1.x * ld;
+            float *g2 = prm.P + (size_t)r2.x * ld, *g3 = prm.P + (size_t)r3.x * ld;
+#pragma unroll
+            for (int v = 0; v < NVR; ++v) {
+                const int c = lc + 128 * v;
+                const bool in = c < F;
+                float4 qv = q.v[v];
+                float4 n0 = axmby(ap, p0.v[v], lp * e0, qv);
+                qv = axmby(aq, qv, lq * e0, p0.v[v]);
+                float4 n1 = axmby(ap, p1.v[v], lp * e1, qv);
+                qv = axmby(aq, qv, lq * e1, p1.v[v]);
+                float4 n2 = axmby(ap, p2.v[v], lp * e2, qv);
+                qv = axmby(aq, qv, lq * e2, p2.v[v]);
+                float4 n3 = axmby(ap, p3.v[v], lp * e3, qv);
+                qv = axmby(aq, qv, lq * e3, p3.v[v]);
+                q.v[v] = qv;
+                if (prm.upd_user && in) {
+                    *reinterpret_cast<float4 *>(g0 + c) = n0;
+                    *reinterpret_cast<float4 *>(g1 + c) = n1;
+                    *reinterpret_cast<float4 *>(g2 + c) = n2;
+                    *reinterpret_cast<float4 *>(g3 + c) = n3;
+                }
+            }
+            if (prm.upd_user) {
+                prm.bu[u] = fmaf(-lp, e0, ap * ub0);
+                prm.bu[r1.x] = fmaf(-lp, e1, ap * ub1);
+                prm.bu[r2.x] = fmaf(-lp, e2, ap * ub2);
+                prm.bu[r3.x] = fmaf(-lp, e3, ap * ub3);
+                ring.dirty = true;
+            }
+            ib = fmaf(-lq, e0, aq * ib);
+            ib = fmaf(-lq, e1, aq * ib);
+            ib = fmaf(-lq, e2, aq * ib);
+            ib = fmaf(-lq, e3, aq * ib);
+            k += 4u;
+            ++n_quads;
+            PROF_ADD(5);
+        } else {
+            // ---- single rating
             Row<NVR> p;
             float ub = 0.f;
-            if (have_next) {
-                p = pn;
-                ub = ubn;
-            } else {
-                if (NV > 0) load_row_strong<NVR>(p, prm.P + (size_t)u * prm.ld, lane, prm.F);
+            if (ctrl & kCtrlDup) {  // recently updated (or last bias chunk): read directly, after our own stores
+                if (NV > 0) load_row_strong<NVR>(p, prm.P + (size_t)u * ld, lane, F);
                 if (has_bias) ub = ld_strong_f(prm.bu + u);
+            } else {
+                cp_async_wait_dyn((int)(pf - 1u - k));
+                if (has_bias) __syncwarp();
+                PROF_ADD(3);
+                const float *sl = slot_of(k);
+#pragma unroll
+                for (int v = 0; v < NVR; ++v)
+                    if (NV > 0) p.v[v] = *reinterpret_cast<const float4 *>(sl + lc + 128 * v);
+                if (has_bias) ub = sl[128 * NV + (u & 3)];
             }
-            if (it != cur_item) {
-                flush_q();
-                cur_item = it;
-                if (QSMEM) {
-                    if (NV > 0) load_row<NVR>(q, sq + (size_t)it * prm.ld, lane, prm.F);
-                    ib = sbi[it];
-                } else {
-                    if (NV > 0) load_row<NVR>(q, prm.Q + (size_t)it * prm.ld, lane, prm.F);
-                    ib = has_bias ? prm.bi[it] : 0.f;
-                }
-            }
-            // ---- prefetch the next rating's user row if its stripe is already released
-            have_next = false;
-            int32_t u1 = -1;
-            if (j + 1 < cnt) {
-                const int32_t s1 = __shfl_sync(0xffffffffu, rs, j + 1);
-                u1 = __shfl_sync(0xffffffffu, ru, j + 1);
-                if (s1 <= ring.rel) {
-                    have_next = true;
-                    if (u1 != u) {
-                        if (NV > 0) load_row_strong<NVR>(pn, prm.P + (size_t)u1 * prm.ld, lane, prm.F);
-                        if (has_bias) ubn = ld_strong_f(prm.bu + u1);
-                    }
-                }
-            }
-            // ---- update
+            const float r = __int_as_float(rc.z);
             if (NV > 0) {
                 sgd_step<KERNEL, NVR>(p, q, ub, ib, r, prm);
             } else {
@@ -348,18 +620,35 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
                 if (prm.upd_item) ib += prm.lr * (err - prm.reg * ib);
             }
             if (prm.upd_user) {
-                if (NV > 0) store_row<NVR>(p, prm.P + (size_t)u * prm.ld, lane, prm.F);
+                if (NV > 0) store_row<NVR>(p, prm.P + (size_t)u * ld, lane, F);
                 if (has_bias) prm.bu[u] = ub;  // every lane stores the same value (own program order)
                 ring.dirty = true;
             }
-            if (have_next && u1 == u) {  // same user again: forward the fresh row in registers
-                pn = p;
-                ubn = ub;
-            }
+            k += 1u;
+            ++n_singles;
+            PROF_ADD(6);
         }
+        if (k >= w0 + 32u) {  // slide the record window: the half [w0, w0+32) is dead
+            srec[(w0 + lane) & 63u] = next_rec;
+            w0 += 32u;
+            const uint32_t nx = w0 + 64u + lane;
+            next_rec = (nx < n_list) ? __ldcs(recs + nx) : rec_none;
+            __syncwarp();
+        }
+        PROF_ADD(7);
     }
     flush_q();
+    const long long clk_work = clock64();
     ring.finish(rv.W);
+    if (rv.stats && lane == 0) {
+        rv.stats[4 * (int64_t)w + 0] = clk_work - clk_start;
+        rv.stats[4 * (int64_t)w + 1] = ring.wait_cycles;
+        rv.stats[4 * (int64_t)w + 2] = n_quads;
+        rv.stats[4 * (int64_t)w + 3] = n_singles;
+#if MFK_RING_PROFILE
+        for (int j = 0; j < 8; ++j) rv.prof[8 * (int64_t)w + j] = prof[j];
+#endif
+    }
 
     if (QSMEM && prm.upd_item) {
         __syncwarp();
@@ -368,8 +657,8 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
             if (it < 0) continue;
             if (NV > 0) {
                 Row<NVR> t;
-                load_row<NVR>(t, sq + (size_t)s * prm.ld, lane, prm.F);
-                store_row<NVR>(t, prm.Q + (size_t)it * prm.ld, lane, prm.F);
+                load_row<NVR>(t, sq + (size_t)s * ld, lane, F);
+                store_row<NVR>(t, prm.Q + (size_t)it * ld, lane, F);
             }
             if (has_bias && lane == 0) prm.bi[it] = sbi[s];
         }
@@ -377,19 +666,25 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
 }
 
 template <int KERNEL, int NV, bool QSMEM>
-static int launch_ring(const mfk_plan *plan, const SgdParams &prm, size_t smem, cudaStream_t st) {
+static int launch_ring(const mfk_plan *plan, const SgdParams &prm, int depth, size_t smem, cudaStream_t st) {
     RingView rv;
-    rv.su = plan->su;
-    rv.si = plan->si;
-    rv.sslot = plan->sslot;
-    rv.sstep = plan->sstep;
-    rv.sr = plan->sr;
+    rv.rec = plan->rec;
     rv.wbeg = plan->wbeg;
     rv.witems = plan->witems;
     rv.flags = plan->flags;
     rv.W = plan->W;
     rv.k = plan->warps_per_cta;
     rv.max_slots = plan->max_slots;
+    rv.depth = depth;
+    rv.stats = plan->stats;
+    rv.prof = plan->stats + 4 * (size_t)plan->W;
+    {
+        static const long long wd_ms = [] {
+            const char *e = getenv("MFK_RING_WATCHDOG_MS");
+            return e ? atoll(e) : 10000ll;
+        }();
+        rv.watchdog_ns = wd_ms > 0 ? (unsigned long long)wd_ms * 1000000ull : 0ull;
+    }
     auto kern = k_sgd_ring<KERNEL, NV, QSMEM>;
     if (plan->warps_per_cta * 32 > ring_max_threads<NV>()) {
         set_error("sgd ring: plan has %d warps per CTA but rows of %d floats allow at most %d; rebuild the plan with "
@@ -403,8 +698,8 @@ static int launch_ring(const mfk_plan *plan, const SgdParams &prm, size_t smem, 
     int rc = device_props(&props);
     if (rc) return rc;
     if ((int64_t)per_sm * props.sm_count < plan->n_ctas) {
-        set_error("sgd ring: %d CTAs of %d warps cannot be co-resident (%d per SM x %d SMs)", plan->n_ctas,
-                  plan->warps_per_cta, per_sm, props.sm_count);
+        set_error("sgd ring: %d CTAs of %d warps (%zu B smem) cannot be co-resident (%d per SM x %d SMs)",
+                  plan->n_ctas, plan->warps_per_cta, smem, per_sm, props.sm_count);
         return MFK_ERR_UNSUPPORTED;
     }
     SgdParams prm_copy = prm;
@@ -415,15 +710,25 @@ static int launch_ring(const mfk_plan *plan, const SgdParams &prm, size_t smem, 
     return MFK_OK;
 }
 
+// Shared memory plan: Q stripe in smem if it fits next to a ring of depth >= 4, else Q stays in global/L2.
 template <int KERNEL, int NV>
 static int launch_ring_q(const mfk_plan *plan, const SgdParams &prm, cudaStream_t st) {
     DeviceProps props;
     int rc = device_props(&props);
     if (rc) return rc;
-    size_t per_warp = ((size_t)plan->max_slots * (size_t)(prm.ld + 1) + 3) & ~(size_t)3;
-    size_t smem_q = 128 + per_warp * sizeof(float) * (size_t)plan->warps_per_cta;
-    if (smem_q + 1024 <= props.smem_optin) return launch_ring<KERNEL, NV, true>(plan, prm, smem_q, st);
-    return launch_ring<KERNEL, NV, false>(plan, prm, 128, st);
+    const size_t budget = props.smem_optin > 2048 ? props.smem_optin - 1024 : 0;
+    const size_t k = (size_t)plan->warps_per_cta;
+    const size_t q_floats = ((size_t)plan->max_slots * (size_t)(prm.ld + 1) + 3) & ~(size_t)3;
+    const size_t slot_floats = 128 * (size_t)NV + 4;  // full-width ring slots (zero beyond F)
+    auto bytes = [&](bool qsmem, int d) {
+        return 128 + 4 * k * ((qsmem ? q_floats : 0) + (size_t)d * slot_floats + 256 /* record window */);
+    };
+    for (int d = kRingDepthMax; d >= 4; d >>= 1)
+        if (bytes(true, d) <= budget) return launch_ring<KERNEL, NV, true>(plan, prm, d, bytes(true, d), st);
+    for (int d = kRingDepthMax; d >= 2; d >>= 1)
+        if (bytes(false, d) <= budget) return launch_ring<KERNEL, NV, false>(plan, prm, d, bytes(false, d), st);
+    set_error("sgd ring: no shared-memory configuration fits (%d warps/CTA, ld=%d)", plan->warps_per_cta, prm.ld);
+    return MFK_ERR_UNSUPPORTED;
 }
 
 template <int KERNEL>
@@ -464,7 +769,8 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
     MFK_REQUIRE(d_P && d_Q && d_bu && d_bi, "mfk_kmf_sgd_epoch: null parameter array");
     MFK_REQUIRE(n_factors >= 1, "mfk_kmf_sgd_epoch: n_factors must be >= 1");
     MFK_REQUIRE(ld >= n_factors && ld % 4 == 0, "mfk_kmf_sgd_epoch: ld=%d must be >= n_factors and a multiple of 4", ld);
-    MFK_REQUIRE((((uintptr_t)d_P | (uintptr_t)d_Q) & 15) == 0, "mfk_kmf_sgd_epoch: P/Q must be 16-byte aligned");
+    MFK_REQUIRE((((uintptr_t)d_P | (uintptr_t)d_Q | (uintptr_t)d_bu) & 15) == 0,
+                "mfk_kmf_sgd_epoch: P/Q/bu must be 16-byte aligned");
     if (n_factors > MFK_MAX_FACTORS) {
         set_error("mfk_kmf_sgd_epoch: n_factors=%d > %d unsupported", n_factors, MFK_MAX_FACTORS);
         return MFK_ERR_UNSUPPORTED;
@@ -478,6 +784,7 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
     prm.bi = d_bi;
     prm.F = (n_factors + 3) & ~3;
     prm.ld = ld;
+    prm.n_users = plan->n_users;
     prm.mu = global_mean;
     prm.lr = lr;
     prm.reg = reg;
@@ -498,6 +805,7 @@ extern "C" int mfk_bias_sgd_epoch(mfk_plan *plan, float *d_bu, float *d_bi, floa
                                   int update_user_params, int update_item_params, void *stream) {
     MFK_REQUIRE(plan != nullptr, "mfk_bias_sgd_epoch: plan is NULL");
     MFK_REQUIRE(d_bu && d_bi, "mfk_bias_sgd_epoch: null parameter array");
+    MFK_REQUIRE(((uintptr_t)d_bu & 15) == 0, "mfk_bias_sgd_epoch: bu must be 16-byte aligned");
     if (plan->n == 0) return MFK_OK;
     cudaStream_t st = as_stream(stream);
     SgdParams prm;
@@ -507,6 +815,7 @@ extern "C" int mfk_bias_sgd_epoch(mfk_plan *plan, float *d_bu, float *d_bi, floa
     prm.bi = d_bi;
     prm.F = 0;
     prm.ld = 0;
+    prm.n_users = plan->n_users;
     prm.mu = global_mean;
     prm.lr = lr;
     prm.reg = reg;

@@ -97,6 +97,16 @@ class Plan:
         check(lib().mfk_plan_assignment(self._h, ptr(w), ptr(s), stream_ptr()))
         return w, s
 
+    def stats(self):
+        """[n_workers, 4] int64 host array: cycles, blocked cycles, 4-chains, singles of the last epoch."""
+        torch = _torch()
+        W = self.info()["n_workers"]
+        out = torch.empty((12 * W,), dtype=torch.int64, device=device())
+        check(lib().mfk_plan_stats(self._h, ptr(out), stream_ptr()))
+        out = out.cpu().numpy()
+        self.last_profile = out[4 * W:].reshape(W, 8)  # phase counters (MFK_RING_PROFILE builds only)
+        return out[:4 * W].reshape(W, 4)
+
     def close(self):
         if getattr(self, "_h", None) is not None and self._h.value:
             lib().mfk_plan_destroy(self._h)
