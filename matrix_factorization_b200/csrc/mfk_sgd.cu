@@ -177,9 +177,9 @@ __device__ __forceinline__ void store_row(const Row<NV> &x, float *row, int lane
     }
 }
 
-__device__ __forceinline__ void cp_async16(float *smem_dst, const float *gsrc) {
-    uint32_t d = (uint32_t)__cvta_generic_to_shared(smem_dst);
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(d), "l"(gsrc) : "memory");
+// dst is a 32-bit shared-window address (computed once per warp: the generic->shared conversion is not free)
+__device__ __forceinline__ void cp_async16(uint32_t smem_dst, const float *gsrc) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_dst), "l"(gsrc) : "memory");
 }
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 // wait until at most n of this thread's cp.async groups are pending (n is warp-uniform, 0..7)
@@ -446,20 +446,20 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
     // ---- prefetch ring: index x lives in slot x & (D-1); one cp.async group per index
     uint32_t pf = 0;  // next index to issue
     auto slot_of = [&](uint32_t x) { return sring + (x & dmask) * RS; };
+    const uint32_t sring_s = (uint32_t)__cvta_generic_to_shared(sring);
+    auto slot_s = [&](uint32_t x) { return sring_s + (x & dmask) * (RS * 4u); };  // byte address in the shared window
     auto issue_row = [&](uint32_t x, int32_t u, int32_t ctl) {  // the row only; closes the index's group
         if (NV > 0 && !(ctl & kCtrlDup)) {
-            float *slot = slot_of(x);
-            const float *row = prm.P + (size_t)u * ld;
+            const uint32_t slot = slot_s(x) + 4u * (uint32_t)lc;
+            const float *row = prm.P + (size_t)u * ld + lc;
 #pragma unroll
-            for (int j = 0; j < NVR; ++j) {
-                int c = lc + 128 * j;
-                if (c < F) cp_async16(slot + c, row + c);
-            }
+            for (int j = 0; j < NVR; ++j)
+                if (lc + 128 * j < F) cp_async16(slot + 512u * j, row + 128 * j);
         }
         cp_async_commit();
     };
     auto issue = [&](uint32_t x, int32_t u, int32_t ctl) {
-        if (has_bias && lane == 0 && !(ctl & kCtrlDup)) cp_async16(slot_of(x) + 128 * NV, prm.bu + (u & ~3));
+        if (has_bias && lane == 0 && !(ctl & kCtrlDup)) cp_async16(slot_s(x) + 512u * NV, prm.bu + (u & ~3));
         issue_row(x, u, ctl);
     };
 
@@ -486,7 +486,7 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
                     if (has_bias && lane < 4) {  // the four bias chunks with one instruction (lane j -> index pf+j)
                         const int32_t uj = lane == 0 ? a0.x : (lane == 1 ? a1.x : (lane == 2 ? a2.x : a3.x));
                         const int32_t cj = lane == 0 ? a0.w : (lane == 1 ? a1.w : (lane == 2 ? a2.w : a3.w));
-                        if (!(cj & kCtrlDup)) cp_async16(slot_of(pf + (uint32_t)lane) + 128 * NV, prm.bu + (uj & ~3));
+                        if (!(cj & kCtrlDup)) cp_async16(slot_s(pf + (uint32_t)lane) + 512u * NV, prm.bu + (uj & ~3));
                     }
                     issue_row(pf, a0.x, a0.w);
                     issue_row(pf + 1u, a1.x, a1.w);

@@ -1,0 +1,147 @@
+"""
+Multi-GPU DSGD for KernelMF: one process per GPU, torch.distributed for the plumbing.
+
+Users are dealt into G nnz-balanced stripes (rank g owns stripe g of P, the user biases and the
+ratings of its users, pre-split into G item blocks); items are dealt into G stripes.  At sub-epoch
+s rank g holds item stripe (g + s) mod G and runs the single-GPU stratified kernel on block
+(g, (g + s) mod G); then every rank sends its item stripe (factors + biases) to rank g-1 and
+receives the next one from rank g+1 (ring shift over NVLink / NVSwitch).  G sub-epochs = 1 epoch.
+Blocks in flight never share a user or an item, so the step-major order of the G block plans,
+concatenated sub-epoch by sub-epoch, is a valid sequential replay order.
+
+The host-side partitioning logic (`partition`) is pure numpy and is what the gloo CPU tests
+exercise; `DsgdTrainer` needs CUDA + NCCL.
+"""
+from __future__ import annotations
+
+import math
+
+import numpy as np
+
+
+def deal_balanced(deg: np.ndarray, n_bins: int):
+    """Snake-deal ids by descending degree into n_bins (nnz balance).  Returns (bin_of, local_index)."""
+    order = np.argsort(-deg, kind="stable")
+    rnd, pos = np.divmod(np.arange(len(deg)), n_bins)
+    b = np.where(rnd % 2 == 1, n_bins - 1 - pos, pos)
+    bin_of = np.empty(len(deg), dtype=np.int64)
+    local = np.empty(len(deg), dtype=np.int64)
+    bin_of[order] = b
+    local[order] = rnd
+    return bin_of, local
+
+
+def partition(u: np.ndarray, i: np.ndarray, n_users: int, n_items: int, G: int):
+    """Stripe assignment for G ranks.  Returns dict with per-user / per-item (stripe, local id), stripe
+    sizes and, per rating, its block (user stripe, item stripe)."""
+    du = np.bincount(u, minlength=n_users)
+    di = np.bincount(i, minlength=n_items)
+    us, ul = deal_balanced(du, G)
+    is_, il = deal_balanced(di, G)
+    return {
+        "user_stripe": us, "user_local": ul, "item_stripe": is_, "item_local": il,
+        "users_per_stripe": np.bincount(us, minlength=G), "items_per_stripe": np.bincount(is_, minlength=G),
+        "block_u": us[u], "block_i": is_[i],
+    }
+
+
+def subepoch_schedule(G: int):
+    """[(sub-epoch s, [(rank g, item stripe j), ...])]: the G blocks processed concurrently in each sub-epoch."""
+    return [(s, [(g, (g + s) % G) for g in range(G)]) for s in range(G)]
+
+
+class DsgdTrainer:
+    """Rank-local state of a G-GPU DSGD fit.  Construct on every rank with the ratings of the rank's
+    user stripe (local user ids, GLOBAL item stripe / local item ids)."""
+
+    def __init__(self, rank: int, world: int, u_local, item_stripe, item_local, r, n_users_local: int,
+                 items_per_stripe, n_factors: int, P, Q_stripe, bu, bi_stripe, device):
+        import torch
+        from . import engine
+
+        self.rank, self.G, self.F = rank, world, n_factors
+        self.device = device
+        self.P, self.bu = P, bu
+        self.n = int(u_local.numel())
+        ld = P.shape[1]
+        self.max_items = int(max(items_per_stripe))
+        # two item-stripe buffers (current + incoming), each [max_items, ld + 1]: factors then bias column
+        self.qbuf = [torch.zeros((self.max_items, ld + 4), dtype=torch.float32, device=device) for _ in range(2)]
+        self.qbuf[0][: Q_stripe.shape[0], :ld].copy_(Q_stripe)
+        self.qbuf[0][: Q_stripe.shape[0], ld].copy_(bi_stripe)
+        self.cur = 0
+        self.items_per_stripe = [int(x) for x in items_per_stripe]
+        self.ld = ld
+        # one plan per item stripe (block (rank, j))
+        self.plans, self.block_n = [], []
+        self.block_data = []
+        for j in range(world):
+            m = item_stripe == j
+            bu_, bi_, br_ = u_local[m].contiguous(), item_local[m].contiguous(), r[m].contiguous()
+            self.block_data.append((bu_, bi_, br_))
+            self.block_n.append(int(bu_.numel()))
+            self.plans.append(engine.Plan(bu_, bi_, br_, n_users_local, max(1, self.items_per_stripe[j]), n_factors=n_factors))
+        # contiguous Q / bi views the kernel works on (stripe buffers hold [Q | bi] side by side)
+        self.Qwork = torch.zeros((self.max_items, ld), dtype=torch.float32, device=device)
+        self.biwork = torch.zeros((self.max_items,), dtype=torch.float32, device=device)
+        self.sse = torch.zeros((1,), dtype=torch.float64, device=device)
+
+    def epoch(self, kernel, mu, lr, reg, gamma, lo, hi):
+        """One DSGD epoch: G sub-epochs of (local stratified SGD on one block, ring shift of the item stripe)."""
+        import torch
+        import torch.distributed as dist
+        from . import engine
+
+        G, g, ld = self.G, self.rank, self.ld
+        for s in range(G):
+            j = (g + s) % G
+            buf = self.qbuf[self.cur]
+            nj = self.items_per_stripe[j]
+            if self.block_n[j] > 0:
+                self.Qwork[:nj].copy_(buf[:nj, :ld])
+                self.biwork[:nj].copy_(buf[:nj, ld])
+                engine.kmf_sgd_epoch(self.plans[j], kernel, self.P, self.Qwork, self.bu, self.biwork, self.F, mu, lr,
+                                     reg, gamma, lo, hi)
+                buf[:nj, :ld].copy_(self.Qwork[:nj])
+                buf[:nj, ld].copy_(self.biwork[:nj])
+            if G > 1:
+                nxt = self.qbuf[1 - self.cur]
+                ops = [dist.P2POp(dist.isend, buf, (g - 1) % G), dist.P2POp(dist.irecv, nxt, (g + 1) % G)]
+                for w in dist.batch_isend_irecv(ops):
+                    w.wait()
+                self.cur = 1 - self.cur
+        # after G shifts every stripe is back on its home rank: rank g holds stripe g again
+
+    def sse_epoch(self, kernel, mu, gamma, lo, hi):
+        """Sum of squared errors of the rank's ratings: all-gather the item stripes, one SSE pass per block."""
+        import torch
+        import torch.distributed as dist
+        from . import engine
+
+        G, ld = self.G, self.ld
+        mine = self.qbuf[self.cur]
+        if G > 1:
+            allq = [torch.empty_like(mine) for _ in range(G)]
+            dist.all_gather(allq, mine)
+        else:
+            allq = [mine]
+        total = torch.zeros((1,), dtype=torch.float64, device=self.device)
+        for j in range(G):
+            if self.block_n[j] == 0:
+                continue
+            nj = self.items_per_stripe[j]
+            self.Qwork[:nj].copy_(allq[j][:nj, :ld])
+            self.biwork[:nj].copy_(allq[j][:nj, ld])
+            bu_, bi_, br_ = self.block_data[j]
+            engine.kmf_sse(kernel, bu_, bi_, br_, self.P, self.Qwork, self.bu, self.biwork, self.F, mu, gamma, lo, hi,
+                           self.sse)
+            total += self.sse
+        if G > 1:
+            dist.all_reduce(total)
+        return total
+
+    def home_stripe(self):
+        """(Q stripe [n_items_of_stripe, ld], bi stripe) of this rank's home item stripe."""
+        buf = self.qbuf[self.cur]
+        nj = self.items_per_stripe[self.rank]
+        return buf[:nj, : self.ld], buf[:nj, self.ld]
