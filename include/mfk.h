@@ -175,6 +175,13 @@ int mfk_score_topk(int kernel, const int32_t *d_users, int64_t m, const float *d
                    const int32_t *d_mask_items, int32_t k, int bound_ratings, float *d_scores,
                    int32_t *d_items, void *d_ws, void *stream);
 
+/* Merge step of the item-sharded recommend: d_scores_in / d_items_in are [m][c] candidate lists (the
+ * all-gathered per-shard top-k lists: UNBOUNDED scores, global item ids, item < 0 = padding); keeps
+ * the best k per user (score descending, ties by lower item id) and clips if bound_ratings. */
+int mfk_topk_merge(const float *d_scores_in, const int32_t *d_items_in, int64_t m, int32_t c, int32_t k,
+                   int bound_ratings, float min_rating, float max_rating, float *d_scores, int32_t *d_items,
+                   void *stream);
+
 /* ------------------------------------------------------------------------------------
  * Host-buffer entry points (what a cgo / JNI / ctypes binding without torch would call).
  * All pointers are HOST pointers; the call allocates device memory, copies in, runs, copies

@@ -242,9 +242,73 @@ __global__ void __launch_bounds__(kSelThreads) k_select(const uint32_t *__restri
     }
 }
 
+// Merge of per-shard top-k lists (the all-gather step of the item-sharded recommend): one CTA per user
+// sorts its c candidates (score desc, ties -> lower item id; item < 0 = padding) and keeps the best k.
+__global__ void __launch_bounds__(kSelThreads) k_topk_merge(const float *__restrict__ in_scores,
+                                                            const int32_t *__restrict__ in_items, int32_t c,
+                                                            int32_t k, int bound, float lo, float hi,
+                                                            float *out_scores, int32_t *out_items) {
+    extern __shared__ unsigned long long s_sel[];
+    const int tid = threadIdx.x;
+    int cpow2 = 1;
+    while (cpow2 < c) cpow2 <<= 1;
+    const float *sc = in_scores + (size_t)blockIdx.x * c;
+    const int32_t *it = in_items + (size_t)blockIdx.x * c;
+    for (int j = tid; j < cpow2; j += kSelThreads) {
+        unsigned long long key = 0ull;
+        if (j < c && it[j] >= 0) key = ((unsigned long long)f2key(sc[j]) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)it[j]);
+        s_sel[j] = key;
+    }
+    __syncthreads();
+    for (int size = 2; size <= cpow2; size <<= 1) {
+        for (int stride = size >> 1; stride > 0; stride >>= 1) {
+            for (int t = tid; t < cpow2 / 2; t += kSelThreads) {
+                int lo_i = 2 * t - (t & (stride - 1));
+                int hi_i = lo_i + stride;
+                bool desc = ((lo_i & size) == 0);
+                unsigned long long x = s_sel[lo_i], y = s_sel[hi_i];
+                if ((x < y) == desc) {
+                    s_sel[lo_i] = y;
+                    s_sel[hi_i] = x;
+                }
+            }
+            __syncthreads();
+        }
+    }
+    for (int j = tid; j < k; j += kSelThreads) {
+        float score = -INFINITY;
+        int32_t item = -1;
+        unsigned long long ck = j < cpow2 ? s_sel[j] : 0ull;
+        if (ck != 0ull) {
+            item = (int32_t)(0xffffffffu - (uint32_t)(ck & 0xffffffffull));
+            score = key2f((uint32_t)(ck >> 32));
+            if (bound) score = score > hi ? hi : (score < lo ? lo : score);
+        }
+        out_scores[(size_t)blockIdx.x * k + j] = score;
+        out_items[(size_t)blockIdx.x * k + j] = item;
+    }
+}
+
 }  // namespace mfk
 
 using namespace mfk;
+
+extern "C" int mfk_topk_merge(const float *d_scores_in, const int32_t *d_items_in, int64_t m, int32_t c, int32_t k,
+                              int bound_ratings, float min_rating, float max_rating, float *d_scores,
+                              int32_t *d_items, void *stream) {
+    MFK_REQUIRE(m >= 0 && c >= 1 && c <= 8192 && k >= 1 && k <= c, "mfk_topk_merge: bad sizes (m=%lld c=%d k=%d)",
+                (long long)m, c, k);
+    if (m == 0) return MFK_OK;
+    MFK_REQUIRE(d_scores_in && d_items_in && d_scores && d_items, "mfk_topk_merge: null array");
+    int cpow2 = 1;
+    while (cpow2 < c) cpow2 <<= 1;
+    size_t smem = sizeof(unsigned long long) * (size_t)cpow2;
+    if (smem > 48 * 1024) MFK_CUDA(cudaFuncSetAttribute(k_topk_merge, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    k_topk_merge<<<(unsigned)m, kSelThreads, smem, as_stream(stream)>>>(d_scores_in, d_items_in, c, k, bound_ratings,
+                                                                      min_rating, max_rating, d_scores, d_items);
+    MFK_LAUNCH_CHECK();
+    return MFK_OK;
+}
 
 extern "C" size_t mfk_score_workspace_bytes(int64_t m, int32_t n_items, int32_t k) {
     (void)k;

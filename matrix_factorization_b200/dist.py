@@ -145,3 +145,49 @@ class DsgdTrainer:
         buf = self.qbuf[self.cur]
         nj = self.items_per_stripe[self.rank]
         return buf[:nj, : self.ld], buf[:nj, self.ld]
+
+
+def sharded_topk(kernel, users, P, bu, Q_local, bi_local, local_to_global, n_factors, mu, gamma, lo, hi, k, bound,
+                 mask_ptr=None, mask_items_global=None, global_to_local=None, group=None):
+    """
+    Item-sharded recommend: every rank scores ALL requested users against ITS item
+    stripe (local top-k with the known-item mask restricted to the stripe), the per-rank lists are
+    all-gathered and merged (score desc, ties by lower global item id), then clipped.
+    users int32 [m] (global user ids, P / bu replicated); Q_local [n_local, ld]; local_to_global int32
+    [n_local]; mask in CSR form over GLOBAL item ids with global_to_local int32 [n_items] (-1 = not
+    on this rank).  Returns (scores [m, k], items [m, k] global ids) on every rank.
+    """
+    import torch
+    import torch.distributed as dist
+    from . import engine
+
+    m = int(users.numel())
+    n_local = int(Q_local.shape[0])
+    k_loc = max(1, min(k, n_local))
+    mp = mi = None
+    if mask_ptr is not None:
+        loc = global_to_local[mask_items_global.long()]
+        keep = loc >= 0
+        # rows keep their CSR structure: count kept entries per row
+        row = torch.repeat_interleave(torch.arange(m, device=users.device), (mask_ptr[1:] - mask_ptr[:-1]))
+        mi = loc[keep].int().contiguous()
+        if mi.numel() == 0:
+            mi = torch.zeros((1,), dtype=torch.int32, device=users.device)
+        mp = torch.zeros(m + 1, dtype=torch.int64, device=users.device)
+        mp[1:] = torch.cumsum(torch.bincount(row[keep], minlength=m), 0)
+    sc, it = engine.score_topk(kernel, users, P, Q_local, bu, bi_local, n_local, n_factors, mu, gamma, lo, hi, k_loc,
+                               False, mp, mi)
+    valid = it >= 0
+    git = torch.where(valid, local_to_global[it.clamp(min=0).long()].int(), torch.full_like(it, -1))
+    if k_loc < k:  # pad to a common width
+        pad = k - k_loc
+        sc = torch.cat([sc, torch.full((m, pad), float("-inf"), device=sc.device)], 1)
+        git = torch.cat([git, torch.full((m, pad), -1, dtype=torch.int32, device=sc.device)], 1)
+    world = dist.get_world_size(group) if dist.is_initialized() else 1
+    if world > 1:
+        all_sc = [torch.empty_like(sc) for _ in range(world)]
+        all_it = [torch.empty_like(git) for _ in range(world)]
+        dist.all_gather(all_sc, sc.contiguous(), group=group)
+        dist.all_gather(all_it, git.contiguous(), group=group)
+        sc, git = torch.cat(all_sc, 1).contiguous(), torch.cat(all_it, 1).contiguous()
+    return engine.topk_merge(sc, git, k, bound, lo, hi)

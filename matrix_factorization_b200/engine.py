@@ -239,3 +239,14 @@ def score_topk(kernel: str, users, P, Q, bu, bi, n_items, n_factors, mu, gamma, 
                                ptr(mask_ptr), ptr(mask_items), int(k), int(bool(bound)), ptr(scores), ptr(items),
                                ptr(ws), stream_ptr()))
     return scores, items
+
+
+def topk_merge(scores_in, items_in, k, bound, lo, hi):
+    """[m, c] candidate lists (unbounded scores, global item ids, -1 padding) -> best k per row."""
+    torch = _torch()
+    m, c = scores_in.shape
+    scores = torch.empty((m, k), dtype=torch.float32, device=device())
+    items = torch.empty((m, k), dtype=torch.int32, device=device())
+    check(lib().mfk_topk_merge(ptr(scores_in), ptr(items_in), int(m), int(c), int(k), int(bool(bound)), float(lo),
+                               float(hi), ptr(scores), ptr(items), stream_ptr()))
+    return scores, items
