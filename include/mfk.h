@@ -163,11 +163,13 @@ int mfk_bias_predict(const int32_t *d_u, const int32_t *d_i, int64_t n, const fl
  * For each of the m users in d_users: score every item with the model's kernel (UNBOUNDED),
  * drop the user's masked items, keep the top k (descending score, ties by lower item id),
  * then clip if bound_ratings.  Masked items of user j are d_mask_items[d_mask_ptr[j] ..
- * d_mask_ptr[j+1]) (internal item ids, any order); d_mask_ptr may be NULL for no mask.
+ * d_mask_ptr[j+1]) (internal item ids, sorted ascending inside each row); d_mask_ptr may be NULL for no mask.
+ * For k <= 64 the contraction runs on the tensor cores (tcgen05, split-TF32, TMA) with mask and top-k
+ * fused into the epilogue; larger k (or MFK_SCORE_SIMT=1) use the fp32 SIMT path.
  * Output rows are padded with item -1 / score -inf when fewer than k candidates remain.
- * d_ws: workspace of mfk_score_workspace_bytes(m, n_items, k) bytes.
+ * d_ws: workspace of mfk_score_workspace_bytes(m, n_items, n_factors, k) bytes.
  * ---------------------------------------------------------------------------------- */
-size_t mfk_score_workspace_bytes(int64_t m, int32_t n_items, int32_t k);
+size_t mfk_score_workspace_bytes(int64_t m, int32_t n_items, int32_t n_factors, int32_t k);
 int mfk_score_topk(int kernel, const int32_t *d_users, int64_t m, const float *d_P,
                    const float *d_Q, const float *d_bu, const float *d_bi, int32_t n_items,
                    int32_t n_factors, int32_t ld, float global_mean, float gamma,

@@ -64,7 +64,7 @@ SIGNATURES = {
     "mfk_bias_als_epoch": (_int, [_p, _p, _p, _f32, _f32, _p]),
     "mfk_bias_sse": (_int, [_p, _p, _p, _i64, _p, _p, _f32, _p, _p, _p]),
     "mfk_bias_predict": (_int, [_p, _p, _i64, _p, _p, _f32, _f32, _f32, _int, _p, _p, _p]),
-    "mfk_score_workspace_bytes": (C.c_size_t, [_i64, _i32, _i32]),
+    "mfk_score_workspace_bytes": (C.c_size_t, [_i64, _i32, _i32, _i32]),
     "mfk_score_topk": (_int, [_int, _p, _i64, _p, _p, _p, _p, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _p, _p, _i32,
                               _int, _p, _p, _p, _p]),
     "mfk_topk_merge": (_int, [_p, _p, _i64, _i32, _i32, _int, _f32, _f32, _p, _p, _p]),

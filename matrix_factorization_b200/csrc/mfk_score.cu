@@ -12,6 +12,7 @@
 // winners.  (The tcgen05 split-TF32 contraction with the top-k fused into its epilogue is the
 // planned replacement of stage 1; the selection semantics stay as they are here.)
 #include <cfloat>
+#include <cstdlib>
 
 #include "mfk_common.cuh"
 
@@ -310,11 +311,29 @@ extern "C" int mfk_topk_merge(const float *d_scores_in, const int32_t *d_items_i
     return MFK_OK;
 }
 
-extern "C" size_t mfk_score_workspace_bytes(int64_t m, int32_t n_items, int32_t k) {
+namespace mfk {
+size_t score_tc_workspace_bytes(int64_t m, int32_t n_items, int32_t n_factors);
+int score_tc(int kernel, const int32_t *d_users, int64_t m, const float *d_P, const float *d_Q, const float *d_bu,
+             const float *d_bi, int32_t n_items, int32_t n_factors, int32_t ld, float mu, float gamma, float lo,
+             float hi, const int64_t *d_mask_ptr, const int32_t *d_mask_items, int32_t k, int bound, float *d_scores,
+             int32_t *d_items, void *d_ws, cudaStream_t st);
+// The tensor-core path serves k <= 64; MFK_SCORE_SIMT=1 forces the fp32 SIMT path (used by the tests to compare).
+static bool use_tensor_path(int32_t k) {
+    static const bool force_simt = [] {
+        const char *e = getenv("MFK_SCORE_SIMT");
+        return e && e[0] == '1';
+    }();
+    return !force_simt && k <= 64;
+}
+}  // namespace mfk
+
+extern "C" size_t mfk_score_workspace_bytes(int64_t m, int32_t n_items, int32_t n_factors, int32_t k) {
     (void)k;
     int64_t tile = m < kScoreUserTile ? m : kScoreUserTile;
     if (tile < 1) tile = 1;
-    return (size_t)tile * (size_t)(n_items > 0 ? n_items : 1) * sizeof(uint32_t);
+    size_t simt = (size_t)tile * (size_t)(n_items > 0 ? n_items : 1) * sizeof(uint32_t);
+    size_t tc = mfk::score_tc_workspace_bytes(m, n_items > 0 ? n_items : 1, n_factors > 0 ? n_factors : 1) + 512;
+    return simt > tc ? simt : tc;
 }
 
 extern "C" int mfk_score_topk(int kernel, const int32_t *d_users, int64_t m, const float *d_P, const float *d_Q,
@@ -332,6 +351,9 @@ extern "C" int mfk_score_topk(int kernel, const int32_t *d_users, int64_t m, con
     MFK_REQUIRE(d_users && d_scores && d_items && d_ws, "mfk_score_topk: null array");
     MFK_REQUIRE(d_mask_ptr == nullptr || d_mask_items != nullptr, "mfk_score_topk: mask_ptr without mask_items");
     cudaStream_t st = as_stream(stream);
+    if (use_tensor_path(k))
+        return score_tc(kernel, d_users, m, d_P, d_Q, d_bu, d_bi, n_items, n_factors, ld, global_mean, gamma, min_rating,
+                        max_rating, d_mask_ptr, d_mask_items, k, bound_ratings, d_scores, d_items, d_ws, st);
     uint32_t *keys = reinterpret_cast<uint32_t *>(d_ws);
     int kpow2 = 1;
     while (kpow2 < k) kpow2 <<= 1;

@@ -1,0 +1,497 @@
+// Scoring on the 5th-generation tensor cores: U_tile x Q^T with split-TF32 (3 MMAs per product: hi*hi +
+// hi*lo + lo*hi, fp32 accumulation in TMEM), TMA-staged 128-byte-swizzled operand tiles, and the known-item
+// mask + per-user top-k fused into the TMEM epilogue -- the score matrix is never written to HBM.
+//
+// Stands in for the predict-all + sort + head of RecommenderBase.recommend (recommender_base.py:245-266)
+// for the linear / sigmoid rank key  b_i + p.q  and the rbf rank key  2 p.q - |q|^2  (SURVEY.md 9.1 item 16).
+//
+// One CTA (192 threads) owns 128 users and walks over all item tiles of 128 items:
+//   warp 0      TMA producer: per k-block of 32 floats loads {U_hi, U_lo, Q_hi, Q_lo} tiles (4 x 16 KB) into a
+//               2-stage shared-memory ring, completion on `full` mbarriers;
+//   warp 1      TMEM allocator + MMA issuer: per k-block 4 x 3 tcgen05.mma.kind::tf32 (M=128, N=128, K=8) into one of
+//               two TMEM accumulators, tcgen05.commit releases the stage / publishes the accumulator;
+//   warps 2..5  epilogue: tcgen05.ld of the thread's row (one user per thread), key = alpha*acc + beta[item],
+//               known-item mask by a cursor over the user's sorted list, threshold test against the row's current
+//               k-th best, sorted insertion of the survivors into the row's top-k list in shared memory.
+#include <cuda.h>
+
+#include <cstdint>
+#include <cstdlib>
+
+#include "mfk_common.cuh"
+
+namespace mfk {
+
+constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 2, TC_KCAP = 64;
+constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;        // 16 KB
+constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;       // U_hi, U_lo, Q_hi, Q_lo
+constexpr int TC_THREADS = 192;
+constexpr int TC_USER_CHUNK = 128 * 256;                // users per workspace chunk
+
+struct TcParams {
+    int32_t m;        // users in this chunk
+    int32_t n_items;
+    int32_t kblocks;  // padded factor count / 32
+    int32_t k;
+    int32_t kernel;
+    float alpha;                 // key = alpha * (p.q) + beta[item]
+    const float *beta;           // [n_pad]   b_i  (linear / sigmoid)  or  -|q|^2 (rbf)
+    const float *unorm;          // [m_pad]   |p|^2 (rbf)
+    const int32_t *users;        // [m]
+    const float *bu;
+    const int64_t *mask_ptr;     // [m + 1] (already offset to this chunk) or null
+    const int32_t *mask_items;   // sorted ascending inside every row
+    float mu, gamma, a, c, lo, hi;
+    int32_t bound;
+    int32_t debug;               // MFK_TC_DEBUG bits: 1 = skip epilogue scan, 2 = skip MMA issue (timing experiments only)
+    float *out_scores;           // [m][k]
+    int32_t *out_items;
+};
+
+// ---------------------------------------------------------------- PTX helpers
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+// bounded wait: a pipeline bug must trap, not hang the GPU
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
+    const uint32_t addr = smem_u32(bar);
+    unsigned long long t0 = 0;
+    for (uint32_t it = 0;; ++it) {
+        uint32_t ok;
+        asm volatile(
+            "{\n\t.reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.b32 %0, 1, 0, p;\n\t}"
+            : "=r"(ok)
+            : "r"(addr), "r"(parity)
+            : "memory");
+        if (ok) return;
+        if ((it & 0xfff) == 0xfff) {
+            unsigned long long now;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+            if (t0 == 0) t0 = now;
+            else if (now - t0 > 4000000000ull) __trap();
+        }
+    }
+}
+__device__ __forceinline__ void tma_load_2d(void *smem_dst, const CUtensorMap *tmap, int32_t x, int32_t y,
+                                            uint64_t *bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+        ::"r"(smem_u32(smem_dst)), "l"(reinterpret_cast<uint64_t>(tmap)), "r"(smem_u32(bar)), "r"(x), "r"(y)
+        : "memory");
+}
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void umma_commit(uint64_t *bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                          uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// K-major operand tile, 128-byte swizzle, 8-row groups 1024 bytes apart (what the TMA box {32 floats, rows} writes)
+__device__ __forceinline__ uint64_t umma_desc_sw128(uint32_t smem_addr) {
+    uint64_t d = 0;
+    d |= (uint64_t)((smem_addr >> 4) & 0x3fff);         // start address
+    d |= (uint64_t)((1024u >> 4) & 0x3fff) << 32;       // stride byte offset
+    d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+    d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+    return d;
+}
+__device__ __forceinline__ uint32_t f2key_tc(float f) {
+    uint32_t b = __float_as_uint(f);
+    return (b & 0x80000000u) ? ~b : (b | 0x80000000u);
+}
+__device__ __forceinline__ float key2f_tc(uint32_t k) {
+    uint32_t b = (k & 0x80000000u) ? (k & 0x7fffffffu) : ~k;
+    return __uint_as_float(b);
+}
+
+// ---------------------------------------------------------------- operand split
+// dst_hi / dst_lo [rows_pad][kp] : tf32-rounded value and the fp32 remainder; optional squared norms.
+__global__ void k_split_rows(const float *__restrict__ src, int32_t ld, int32_t F, const int32_t *__restrict__ rows,
+                             int32_t n_rows, int32_t rows_pad, int32_t kp, float *dst_hi, float *dst_lo, float *norm2) {
+    const int lane = threadIdx.x & 31;
+    int32_t r = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    if (r >= rows_pad) return;
+    const bool live = r < n_rows;
+    const float *s = live ? src + (size_t)(rows ? rows[r] : r) * ld : nullptr;
+    float acc = 0.f;
+    for (int c = lane; c < kp; c += 32) {
+        float x = (live && c < F) ? s[c] : 0.f;
+        uint32_t hb;
+        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(x));
+        float h = __uint_as_float(hb);
+        dst_hi[(size_t)r * kp + c] = h;
+        dst_lo[(size_t)r * kp + c] = x - h;
+        acc = fmaf(x, x, acc);
+    }
+    acc = warp_sum(acc);
+    if (norm2 && lane == 0) norm2[r] = acc;
+}
+
+__global__ void k_make_beta(const float *__restrict__ bi, const float *__restrict__ qnorm, int32_t n_items,
+                            int32_t n_pad, int rbf, float *beta) {
+    int32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+    if (j >= n_pad) return;
+    beta[j] = j < n_items ? (rbf ? -qnorm[j] : bi[j]) : -INFINITY;  // padded columns can never be candidates
+}
+
+// ---------------------------------------------------------------- main kernel
+__global__ void __launch_bounds__(TC_THREADS, 1)
+k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ CUtensorMap tm_ulo,
+           const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo, TcParams p) {
+    extern __shared__ unsigned char smem_dyn[];
+    // 1024-byte aligned operand ring (128B swizzle atoms), then the epilogue's state
+    // (offset arithmetic on the shared array keeps the pointers in the shared address space -> LDS/STS, not generic)
+    unsigned char *base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
+    unsigned char *stage_mem = base;
+    uint32_t *tk_keys = reinterpret_cast<uint32_t *>(base + TC_STAGES * TC_STAGE_BYTES);  // [KCAP][128]
+    int32_t *tk_ids = reinterpret_cast<int32_t *>(tk_keys + TC_KCAP * TC_BM);             // [KCAP][128]
+    float *sbeta = reinterpret_cast<float *>(tk_ids + TC_KCAP * TC_BM);                    // [2][128]
+    float *sscr = sbeta + 2 * TC_BN;                                                       // [32][128] survivor scratch
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sscr + 32 * TC_BM);
+    uint64_t *full = bars, *empty = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const int32_t m0 = blockIdx.x * TC_BM;
+    const int32_t n_tiles = (p.n_items + TC_BN - 1) / TC_BN;
+    const int32_t KB = p.kblocks;
+
+    if (threadIdx.x == 0) {
+        for (int s = 0; s < TC_STAGES; ++s) {
+            mbar_init(full + s, 1);
+            mbar_init(empty + s, 1);
+        }
+        for (int a = 0; a < 2; ++a) {
+            mbar_init(acc_full + a, 1);
+            mbar_init(acc_empty + a, 128);
+        }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    if (warp == 1) {  // TMEM: two 128-column fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+                     : "memory");
+        asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+    }
+    for (int j = threadIdx.x; j < TC_KCAP * TC_BM; j += TC_THREADS) {
+        tk_keys[j] = 0u;
+        tk_ids[j] = -1;
+    }
+    tc_fence_before();
+    __syncthreads();
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
+
+    if (warp == 0) {
+        // ===== TMA producer =====
+        if (lane == 0) {
+            uint32_t stage = 0, phase = 0;
+            for (int32_t nt = 0; nt < n_tiles; ++nt) {
+                for (int32_t kb = 0; kb < KB; ++kb) {
+                    mbar_wait(empty + stage, phase ^ 1u);
+                    unsigned char *st = stage_mem + stage * TC_STAGE_BYTES;
+                    mbar_expect_tx(full + stage, TC_STAGE_BYTES);
+                    tma_load_2d(st, &tm_uhi, kb * TC_BK, m0, full + stage);
+                    tma_load_2d(st + TC_TILE_BYTES, &tm_ulo, kb * TC_BK, m0, full + stage);
+                    tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_qhi, kb * TC_BK, nt * TC_BN, full + stage);
+                    tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_qlo, kb * TC_BK, nt * TC_BN, full + stage);
+                    if (++stage == TC_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+            }
+        }
+    } else if (warp == 1) {
+        // ===== MMA issuer (one elected lane) =====
+        if (lane == 0) {
+            // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
+            const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
+                                   ((uint32_t)(TC_BM >> 4) << 24);
+            uint32_t stage = 0, phase = 0;
+            for (int32_t nt = 0; nt < n_tiles; ++nt) {
+                const uint32_t acc = (uint32_t)nt & 1u;
+                mbar_wait(acc_empty + acc, (((uint32_t)nt >> 1) & 1u) ^ 1u);
+                tc_fence_after();
+                const uint32_t tmem_d = tmem_base + acc * TC_BN;
+                for (int32_t kb = 0; kb < KB; ++kb) {
+                    mbar_wait(full + stage, phase);
+                    tc_fence_after();
+                    const uint32_t sa = smem_u32(stage_mem + stage * TC_STAGE_BYTES);
+                    const uint64_t d_uhi = umma_desc_sw128(sa), d_ulo = umma_desc_sw128(sa + TC_TILE_BYTES);
+                    const uint64_t d_qhi = umma_desc_sw128(sa + 2 * TC_TILE_BYTES), d_qlo = umma_desc_sw128(sa + 3 * TC_TILE_BYTES);
+#pragma unroll
+                    for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
+                        const uint64_t adv = (uint64_t)((k4 * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle atom
+                        if (p.debug & 2) continue;
+                        umma_tf32(tmem_d, d_uhi + adv, d_qhi + adv, idesc, (kb | k4) ? 1u : 0u);
+                        umma_tf32(tmem_d, d_uhi + adv, d_qlo + adv, idesc, 1u);
+                        umma_tf32(tmem_d, d_ulo + adv, d_qhi + adv, idesc, 1u);
+                    }
+                    umma_commit(empty + stage);  // stage reusable once these MMAs have read it
+                    if (++stage == TC_STAGES) {
+                        stage = 0;
+                        phase ^= 1u;
+                    }
+                }
+                umma_commit(acc_full + acc);  // accumulator complete
+            }
+        }
+    } else {
+        // ===== epilogue: thread <-> TMEM lane <-> user row =====
+        const int quad = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) ..
+        const int row = quad * 32 + lane;
+        const int et = (warp - 2) * 32 + lane;  // 0..127 index among the epilogue threads
+        const bool live = (m0 + row) < p.m;
+        const int32_t k = p.k;
+        // known-item mask: the row's sorted list is consumed in item order; the next four ids sit in registers
+        int64_t mcur = 0, me = 0;
+        if (live && p.mask_ptr) {
+            mcur = p.mask_ptr[m0 + row];
+            me = p.mask_ptr[m0 + row + 1];
+        }
+        int32_t mk0 = INT32_MAX, mk1 = INT32_MAX, mk2 = INT32_MAX, mk3 = INT32_MAX;
+        auto mask_refill = [&]() {
+            mk0 = (mcur + 0 < me) ? p.mask_items[mcur + 0] : INT32_MAX;
+            mk1 = (mcur + 1 < me) ? p.mask_items[mcur + 1] : INT32_MAX;
+            mk2 = (mcur + 2 < me) ? p.mask_items[mcur + 2] : INT32_MAX;
+            mk3 = (mcur + 3 < me) ? p.mask_items[mcur + 3] : INT32_MAX;
+        };
+        mask_refill();
+        float thr = -INFINITY;  // score of the row's current k-th best (-inf while the list is not full)
+        for (int32_t nt = 0; nt < n_tiles; ++nt) {
+            const uint32_t acc = (uint32_t)nt & 1u;
+            sbeta[acc * TC_BN + et] = p.beta[nt * TC_BN + et];  // padded columns carry -inf: never candidates
+            mbar_wait(acc_full + acc, ((uint32_t)nt >> 1) & 1u);
+            tc_fence_after();
+            asm volatile("bar.sync 1, 128;" ::: "memory");  // beta tile visible to the 4 epilogue warps
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_BN;
+#pragma unroll 1
+            for (int ch = 0; ch < TC_BN / 32; ++ch) {
+                uint32_t v[32];
+                asm volatile(
+                    "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+                    "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,"
+                    "%27,%28,%29,%30,%31}, [%32];"
+                    : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]),
+                      "=r"(v[8]), "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]),
+                      "=r"(v[16]), "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]),
+                      "=r"(v[24]), "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+                    : "r"(taddr + (uint32_t)(ch * 32))
+                    : "memory");
+                asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+                if (!live || (p.debug & 1)) continue;
+                // pass 1 (branch-free): scores and the bitmask of those above the row's threshold
+                const float4 *bt = reinterpret_cast<const float4 *>(sbeta + acc * TC_BN + ch * 32);
+                uint32_t cand = 0u;
+#pragma unroll
+                for (int j4 = 0; j4 < 8; ++j4) {
+                    const float4 b4 = bt[j4];
+                    float s0 = fmaf(p.alpha, __uint_as_float(v[4 * j4 + 0]), b4.x);
+                    float s1 = fmaf(p.alpha, __uint_as_float(v[4 * j4 + 1]), b4.y);
+                    float s2 = fmaf(p.alpha, __uint_as_float(v[4 * j4 + 2]), b4.z);
+                    float s3 = fmaf(p.alpha, __uint_as_float(v[4 * j4 + 3]), b4.w);
+                    v[4 * j4 + 0] = __float_as_uint(s0);
+                    v[4 * j4 + 1] = __float_as_uint(s1);
+                    v[4 * j4 + 2] = __float_as_uint(s2);
+                    v[4 * j4 + 3] = __float_as_uint(s3);
+                    cand |= (s0 > thr ? 1u : 0u) << (4 * j4 + 0);
+                    cand |= (s1 > thr ? 1u : 0u) << (4 * j4 + 1);
+                    cand |= (s2 > thr ? 1u : 0u) << (4 * j4 + 2);
+                    cand |= (s3 > thr ? 1u : 0u) << (4 * j4 + 3);
+                }
+                if (cand == 0u) continue;
+                // pass 2: the (few) survivors, in item order; their scores are parked in shared memory so that
+                // the loop over set bits can index them
+#pragma unroll
+                for (int j = 0; j < 32; ++j) sscr[j * TC_BM + row] = __uint_as_float(v[j]);
+                while (cand) {
+                    const int j = __ffs(cand) - 1;
+                    cand &= cand - 1u;
+                    const float sc = sscr[j * TC_BM + row];
+                    if (!(sc > thr)) continue;  // the threshold may have risen inside this chunk
+                    const int32_t col = nt * TC_BN + ch * 32 + j;
+                    while (mk0 < col) {  // skip known items that never were candidates
+                        mk0 = mk1; mk1 = mk2; mk2 = mk3; mk3 = INT32_MAX;
+                        ++mcur;
+                        if (mk0 == INT32_MAX && mcur < me) mask_refill();
+                    }
+                    if (mk0 == col) continue;  // known item
+                    const uint32_t key = f2key_tc(sc);
+                    int pos = k - 1;  // sorted insertion; equal keys keep the earlier (lower) item first
+                    while (pos > 0 && tk_keys[(pos - 1) * TC_BM + row] < key) {
+                        tk_keys[pos * TC_BM + row] = tk_keys[(pos - 1) * TC_BM + row];
+                        tk_ids[pos * TC_BM + row] = tk_ids[(pos - 1) * TC_BM + row];
+                        --pos;
+                    }
+                    tk_keys[pos * TC_BM + row] = key;
+                    tk_ids[pos * TC_BM + row] = col;
+                    const uint32_t kth = tk_keys[(k - 1) * TC_BM + row];
+                    thr = kth ? key2f_tc(kth) : -INFINITY;
+                }
+            }
+            tc_fence_before();
+            mbar_arrive(acc_empty + acc);
+        }
+        // ---- winners -> predictions
+        if (live) {
+            const int32_t user = p.users[m0 + row];
+            const float ub = (p.kernel == MFK_KERNEL_RBF) ? 0.f : p.bu[user];
+            const float un = (p.kernel == MFK_KERNEL_RBF) ? p.unorm[m0 + row] : 0.f;
+            for (int j = 0; j < k; ++j) {
+                const uint32_t key = tk_keys[j * TC_BM + row];
+                float score = -INFINITY;
+                int32_t item = -1;
+                if (key != 0u) {
+                    item = tk_ids[j * TC_BM + row];
+                    const float kv = key2f_tc(key);
+                    if (p.kernel == MFK_KERNEL_LINEAR) score = p.mu + ub + kv;
+                    else if (p.kernel == MFK_KERNEL_SIGMOID) score = p.a + p.c * (1.0f / (1.0f + expf(-(p.mu + ub + kv))));
+                    else score = p.a + p.c * expf(-p.gamma * fmaxf(un - kv, 0.f));  // |p-q|^2 = |p|^2 - (2p.q - |q|^2)
+                    if (p.bound) score = score > p.hi ? p.hi : (score < p.lo ? p.lo : score);
+                }
+                p.out_scores[(size_t)(m0 + row) * k + j] = score;
+                p.out_items[(size_t)(m0 + row) * k + j] = item;
+            }
+        }
+    }
+    tc_fence_before();
+    __syncthreads();
+    if (warp == 1) {
+        tc_fence_after();
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+    }
+}
+
+// ---------------------------------------------------------------- host side
+typedef CUresult (*EncodeTiledFn)(CUtensorMap *, CUtensorMapDataType, cuuint32_t, void *, const cuuint64_t *,
+                                  const cuuint64_t *, const cuuint32_t *, const cuuint32_t *, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn encode_fn() {
+    static EncodeTiledFn fn = [] {
+        void *ptr = nullptr;
+        cudaDriverEntryPointQueryResult qres;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &ptr, cudaEnableDefault, &qres) != cudaSuccess ||
+            qres != cudaDriverEntryPointSuccess)
+            ptr = nullptr;
+        return reinterpret_cast<EncodeTiledFn>(ptr);
+    }();
+    return fn;
+}
+
+// [rows][kp] fp32 row-major -> tiles of {32 floats (128 B), 128 rows}, 128-byte swizzle
+static int make_tmap(CUtensorMap *tm, const float *base, int64_t rows, int32_t kp) {
+    EncodeTiledFn fn = encode_fn();
+    if (!fn) {
+        set_error("cuTensorMapEncodeTiled is not available from this driver");
+        return MFK_ERR_CUDA;
+    }
+    cuuint64_t dims[2] = {(cuuint64_t)kp, (cuuint64_t)rows};
+    cuuint64_t strides[1] = {(cuuint64_t)kp * sizeof(float)};
+    cuuint32_t box[2] = {(cuuint32_t)TC_BK, (cuuint32_t)TC_BM};
+    cuuint32_t estr[2] = {1, 1};
+    CUresult r = fn(tm, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 2, const_cast<float *>(base), dims, strides, box, estr,
+                    CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                    CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+    if (r != CUDA_SUCCESS) {
+        set_error("cuTensorMapEncodeTiled failed with CUresult %d", (int)r);
+        return MFK_ERR_CUDA;
+    }
+    return MFK_OK;
+}
+
+static inline int64_t round_up(int64_t x, int64_t m) { return (x + m - 1) / m * m; }
+
+size_t score_tc_workspace_bytes(int64_t m, int32_t n_items, int32_t n_factors) {
+    const int64_t kp = round_up(n_factors, TC_BK);
+    const int64_t mc = round_up(m < TC_USER_CHUNK ? (m > 0 ? m : 1) : TC_USER_CHUNK, TC_BM);
+    const int64_t np = round_up(n_items, TC_BN);
+    return (size_t)(2 * mc * kp + 2 * np * kp + 2 * np + mc + 64) * sizeof(float);
+}
+
+int score_tc(int kernel, const int32_t *d_users, int64_t m, const float *d_P, const float *d_Q, const float *d_bu,
+             const float *d_bi, int32_t n_items, int32_t n_factors, int32_t ld, float mu, float gamma, float lo,
+             float hi, const int64_t *d_mask_ptr, const int32_t *d_mask_items, int32_t k, int bound, float *d_scores,
+             int32_t *d_items, void *d_ws, cudaStream_t st) {
+    const int32_t kp = (int32_t)round_up(n_factors, TC_BK);
+    const int64_t mc_max = round_up(m < TC_USER_CHUNK ? m : TC_USER_CHUNK, TC_BM);
+    const int64_t np = round_up(n_items, TC_BN);
+    float *ws = reinterpret_cast<float *>((reinterpret_cast<uintptr_t>(d_ws) + 255) & ~(uintptr_t)255);
+    float *uhi = ws, *ulo = uhi + mc_max * kp, *qhi = ulo + mc_max * kp, *qlo = qhi + np * kp;
+    float *qnorm = qlo + np * kp, *beta = qnorm + np, *unorm = beta + np;
+    const bool rbf = kernel == MFK_KERNEL_RBF;
+
+    k_split_rows<<<(unsigned)((np * 32 + 255) / 256), 256, 0, st>>>(d_Q, ld, n_factors, nullptr, n_items, (int32_t)np, kp,
+                                                                   qhi, qlo, qnorm);
+    MFK_LAUNCH_CHECK();
+    k_make_beta<<<(unsigned)((np + 255) / 256), 256, 0, st>>>(d_bi, qnorm, n_items, (int32_t)np, rbf ? 1 : 0, beta);
+    MFK_LAUNCH_CHECK();
+    CUtensorMap tm_qhi, tm_qlo;
+    int rc = make_tmap(&tm_qhi, qhi, np, kp);
+    if (rc == MFK_OK) rc = make_tmap(&tm_qlo, qlo, np, kp);
+    if (rc) return rc;
+
+    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_KCAP * TC_BM * 8 + 2 * TC_BN * 4 +
+                        32 * TC_BM * 4 + 128;
+    MFK_CUDA(cudaFuncSetAttribute(k_score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    for (int64_t u0 = 0; u0 < m; u0 += TC_USER_CHUNK) {
+        const int64_t mt = (m - u0 < TC_USER_CHUNK) ? (m - u0) : TC_USER_CHUNK;
+        const int64_t mp = round_up(mt, TC_BM);
+        k_split_rows<<<(unsigned)((mp * 32 + 255) / 256), 256, 0, st>>>(d_P, ld, n_factors, d_users + u0, (int32_t)mt,
+                                                                       (int32_t)mp, kp, uhi, ulo, unorm);
+        MFK_LAUNCH_CHECK();
+        CUtensorMap tm_uhi, tm_ulo;
+        rc = make_tmap(&tm_uhi, uhi, mp, kp);
+        if (rc == MFK_OK) rc = make_tmap(&tm_ulo, ulo, mp, kp);
+        if (rc) return rc;
+        TcParams p;
+        p.m = (int32_t)mt;
+        p.n_items = n_items;
+        p.kblocks = kp / TC_BK;
+        p.k = k;
+        p.kernel = kernel;
+        p.alpha = rbf ? 2.0f : 1.0f;
+        p.beta = beta;
+        p.unorm = unorm;
+        p.users = d_users + u0;
+        p.bu = d_bu;
+        p.mask_ptr = d_mask_ptr ? d_mask_ptr + u0 : nullptr;
+        p.mask_items = d_mask_items;
+        p.mu = mu;
+        p.gamma = gamma;
+        p.a = lo;
+        p.c = hi - lo;
+        p.lo = lo;
+        p.hi = hi;
+        p.bound = bound;
+        {
+            const char *e = getenv("MFK_TC_DEBUG");
+            p.debug = e ? atoi(e) : 0;
+        }
+        p.out_scores = d_scores + (size_t)u0 * k;
+        p.out_items = d_items + (size_t)u0 * k;
+        k_score_tc<<<(unsigned)(mp / TC_BM), TC_THREADS, smem, st>>>(tm_uhi, tm_ulo, tm_qhi, tm_qlo, p);
+        MFK_LAUNCH_CHECK();
+    }
+    return MFK_OK;
+}
+
+}  // namespace mfk

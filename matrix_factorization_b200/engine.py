@@ -233,7 +233,8 @@ def score_topk(kernel: str, users, P, Q, bu, bi, n_items, n_factors, mu, gamma, 
     m = int(users.numel())
     scores = torch.empty((m, k), dtype=torch.float32, device=device())
     items = torch.empty((m, k), dtype=torch.int32, device=device())
-    ws = torch.empty((lib().mfk_score_workspace_bytes(m, int(n_items), int(k)),), dtype=torch.uint8, device=device())
+    ws = torch.empty((lib().mfk_score_workspace_bytes(m, int(n_items), int(n_factors), int(k)),), dtype=torch.uint8,
+                     device=device())
     check(lib().mfk_score_topk(KERNEL_IDS[kernel], ptr(users), m, ptr(P), ptr(Q), ptr(bu), ptr(bi), int(n_items),
                                int(n_factors), int(P.shape[1]), float(mu), float(gamma), float(lo), float(hi),
                                ptr(mask_ptr), ptr(mask_items), int(k), int(bool(bound)), ptr(scores), ptr(items),

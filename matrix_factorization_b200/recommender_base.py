@@ -278,7 +278,7 @@ class RecommenderBase(BaseEstimator, RegressorMixin, metaclass=ABCMeta):
             s = slot[ku]
             sel = s >= 0
             s, ki = s[sel], ki[sel]
-            order = np.argsort(s, kind="stable")
+            order = np.lexsort((ki, s))  # by user slot, item ids ascending inside a row (scoring kernel contract)
             mask_items = ki[order].astype(np.int32)
             mask_ptr = np.zeros(m + 1, dtype=np.int64)
             np.cumsum(np.bincount(s, minlength=m), out=mask_ptr[1:])
