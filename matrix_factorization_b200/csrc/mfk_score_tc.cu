@@ -161,9 +161,9 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
     // (offset arithmetic on the shared array keeps the pointers in the shared address space -> LDS/STS, not generic)
     unsigned char *base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char *stage_mem = base;
-    uint32_t *tk_keys = reinterpret_cast<uint32_t *>(base + TC_STAGES * TC_STAGE_BYTES);  // [KCAP][128]
-    int32_t *tk_ids = reinterpret_cast<int32_t *>(tk_keys + TC_KCAP * TC_BM);             // [KCAP][128]
-    float *sbeta = reinterpret_cast<float *>(tk_ids + TC_KCAP * TC_BM);                    // [2][128]
+    // per-row top-k buffer: composite (sortable score key << 32 | ~item) -- larger = better, unique
+    unsigned long long *tk = reinterpret_cast<unsigned long long *>(base + TC_STAGES * TC_STAGE_BYTES);  // [KCAP][128]
+    float *sbeta = reinterpret_cast<float *>(tk + TC_KCAP * TC_BM);                                       // [2][128]
     float *sscr = sbeta + 2 * TC_BN;                                                       // [32][128] survivor scratch
     uint64_t *bars = reinterpret_cast<uint64_t *>(sscr + 32 * TC_BM);
     uint64_t *full = bars, *empty = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + 2;
@@ -190,10 +190,7 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int j = threadIdx.x; j < TC_KCAP * TC_BM; j += TC_THREADS) {
-        tk_keys[j] = 0u;
-        tk_ids[j] = -1;
-    }
+    for (int j = threadIdx.x; j < TC_KCAP * TC_BM; j += TC_THREADS) tk[j] = 0ull;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -275,7 +272,8 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
             mk3 = (mcur + 3 < me) ? p.mask_items[mcur + 3] : INT32_MAX;
         };
         mask_refill();
-        float thr = -INFINITY;  // score of the row's current k-th best (-inf while the list is not full)
+        float thr = -INFINITY;  // score of the row's current k-th best (-inf while the buffer is not full)
+        int count = 0, minpos = 0;
         for (int32_t nt = 0; nt < n_tiles; ++nt) {
             const uint32_t acc = (uint32_t)nt & 1u;
             sbeta[acc * TC_BN + et] = p.beta[nt * TC_BN + et];  // padded columns carry -inf: never candidates
@@ -334,34 +332,51 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                         if (mk0 == INT32_MAX && mcur < me) mask_refill();
                     }
                     if (mk0 == col) continue;  // known item
-                    const uint32_t key = f2key_tc(sc);
-                    int pos = k - 1;  // sorted insertion; equal keys keep the earlier (lower) item first
-                    while (pos > 0 && tk_keys[(pos - 1) * TC_BM + row] < key) {
-                        tk_keys[pos * TC_BM + row] = tk_keys[(pos - 1) * TC_BM + row];
-                        tk_ids[pos * TC_BM + row] = tk_ids[(pos - 1) * TC_BM + row];
-                        --pos;
+                    // unsorted buffer of the k best: fill, then always replace the current minimum and rescan
+                    // (k independent loads -- no dependent shifting chain)
+                    const unsigned long long ck = ((unsigned long long)f2key_tc(sc) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)col);
+                    const int slot = (count < k) ? count++ : minpos;
+                    tk[slot * TC_BM + row] = ck;
+                    if (count == k) {
+                        unsigned long long mn = ~0ull;
+                        int mp = 0;
+#pragma unroll 4
+                        for (int t = 0; t < k; ++t) {
+                            const unsigned long long x = tk[t * TC_BM + row];
+                            if (x < mn) {
+                                mn = x;
+                                mp = t;
+                            }
+                        }
+                        minpos = mp;
+                        thr = key2f_tc((uint32_t)(mn >> 32));
                     }
-                    tk_keys[pos * TC_BM + row] = key;
-                    tk_ids[pos * TC_BM + row] = col;
-                    const uint32_t kth = tk_keys[(k - 1) * TC_BM + row];
-                    thr = kth ? key2f_tc(kth) : -INFINITY;
                 }
             }
             tc_fence_before();
             mbar_arrive(acc_empty + acc);
         }
-        // ---- winners -> predictions
+        // ---- winners -> predictions: insertion-sort the row's buffer (descending), then emit
         if (live) {
+            for (int i = 1; i < count; ++i) {
+                const unsigned long long x = tk[i * TC_BM + row];
+                int j = i - 1;
+                while (j >= 0 && tk[j * TC_BM + row] < x) {
+                    tk[(j + 1) * TC_BM + row] = tk[j * TC_BM + row];
+                    --j;
+                }
+                tk[(j + 1) * TC_BM + row] = x;
+            }
             const int32_t user = p.users[m0 + row];
             const float ub = (p.kernel == MFK_KERNEL_RBF) ? 0.f : p.bu[user];
             const float un = (p.kernel == MFK_KERNEL_RBF) ? p.unorm[m0 + row] : 0.f;
             for (int j = 0; j < k; ++j) {
-                const uint32_t key = tk_keys[j * TC_BM + row];
                 float score = -INFINITY;
                 int32_t item = -1;
-                if (key != 0u) {
-                    item = tk_ids[j * TC_BM + row];
-                    const float kv = key2f_tc(key);
+                if (j < count) {
+                    const unsigned long long ck = tk[j * TC_BM + row];
+                    item = (int32_t)(0xffffffffu - (uint32_t)(ck & 0xffffffffull));
+                    const float kv = key2f_tc((uint32_t)(ck >> 32));
                     if (p.kernel == MFK_KERNEL_LINEAR) score = p.mu + ub + kv;
                     else if (p.kernel == MFK_KERNEL_SIGMOID) score = p.a + p.c * (1.0f / (1.0f + expf(-(p.mu + ub + kv))));
                     else score = p.a + p.c * expf(-p.gamma * fmaxf(un - kv, 0.f));  // |p-q|^2 = |p|^2 - (2p.q - |q|^2)

@@ -170,11 +170,14 @@ def sharded_topk(kernel, users, P, bu, Q_local, bi_local, local_to_global, n_fac
         keep = loc >= 0
         # rows keep their CSR structure: count kept entries per row
         row = torch.repeat_interleave(torch.arange(m, device=users.device), (mask_ptr[1:] - mask_ptr[:-1]))
-        mi = loc[keep].int().contiguous()
+        # the scoring kernel wants item ids ascending inside each row: sort by (row, local id)
+        rk, lk = row[keep], loc[keep]
+        order = torch.argsort(rk * (n_local + 1) + lk)
+        mi = lk[order].int().contiguous()
         if mi.numel() == 0:
             mi = torch.zeros((1,), dtype=torch.int32, device=users.device)
         mp = torch.zeros(m + 1, dtype=torch.int64, device=users.device)
-        mp[1:] = torch.cumsum(torch.bincount(row[keep], minlength=m), 0)
+        mp[1:] = torch.cumsum(torch.bincount(rk, minlength=m), 0)
     sc, it = engine.score_topk(kernel, users, P, Q_local, bu, bi_local, n_local, n_factors, mu, gamma, lo, hi, k_loc,
                                False, mp, mi)
     valid = it >= 0

@@ -98,3 +98,51 @@ def test_item_sharded_topk_merge_equals_unsharded(G):
                                        0.1, 0.0, 5.0, k, True, mask_ptr, mask_items)
     assert torch.equal(mi, full_i)
     assert torch.allclose(ms, full_s, atol=1e-6)
+
+
+def test_tensor_path_agrees_with_simt_path_on_a_large_shape():
+    """tcgen05 split-TF32 path vs the fp32 SIMT path (forced with MFK_SCORE_SIMT=1 in a subprocess): several user
+    tiles, several k-blocks (F=256), ragged item tile, k=50, per-user masks."""
+    import os
+    import subprocess
+    import sys
+    import tempfile
+
+    code = """
+import sys, numpy as np, torch
+sys.path.insert(0, %r)
+from matrix_factorization_b200 import engine
+rng = np.random.default_rng(11)
+U, I, F, k = 700, 3000, 256, 50
+P, Q = rng.normal(0, 0.2, (U, F)), rng.normal(0, 0.2, (I, F))
+bu, bi = rng.normal(0, 0.2, U), rng.normal(0, 0.2, I)
+users = torch.tensor(rng.permutation(U)[:650].astype(np.int32)).cuda()
+lens = rng.integers(0, 120, 650)
+mp = np.zeros(651, dtype=np.int64); mp[1:] = np.cumsum(lens)
+mi = np.concatenate([np.sort(rng.choice(I, n, replace=False)) for n in lens]).astype(np.int32)
+out = {}
+for kern in ("linear", "rbf"):
+    sc, it = engine.score_topk(kern, users, engine.upload_rows(P), engine.upload_rows(Q), engine.upload_vec(bu),
+                               engine.upload_vec(bi), I, F, 3.0, 0.02, 0.0, 5.0, k, False,
+                               torch.tensor(mp).cuda(), torch.tensor(mi).cuda())
+    out[kern + "_s"] = sc.cpu().numpy(); out[kern + "_i"] = it.cpu().numpy()
+np.savez(sys.argv[1], **out)
+""" % os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    with tempfile.TemporaryDirectory() as d:
+        for tag, env in (("tc", {}), ("simt", {"MFK_SCORE_SIMT": "1"})):
+            f = os.path.join(d, tag + ".npz")
+            subprocess.run([sys.executable, "-c", code, f], check=True, env={**os.environ, **env}, timeout=300)
+            res[tag] = dict(np.load(f))
+    for kern in ("linear", "rbf"):
+        a_s, b_s = res["tc"][kern + "_s"], res["simt"][kern + "_s"]
+        a_i, b_i = res["tc"][kern + "_i"], res["simt"][kern + "_i"]
+        np.testing.assert_allclose(a_s, b_s, atol=2e-5, rtol=0)
+        diff = a_i != b_i
+        # item ids may differ only inside ties within 1e-5 (fp32 summation order differs between the two paths)
+        assert diff.mean() < 0.01
+        rows, cols = np.nonzero(diff)
+        for r, c in zip(rows, cols):
+            if c == a_i.shape[1] - 1:
+                continue  # the k-th place may be tied with the (k+1)-th item, which is outside both lists
+            assert np.sum(np.abs(b_s[r] - b_s[r, c]) < 2e-5) > 1, (kern, r, c)
