@@ -64,7 +64,9 @@ typedef struct {
     int32_t warps_per_cta; /* 0 = choose */
     int32_t n_factors;     /* hint: n_factors the plan will run with (caps warps_per_cta: rows
                               wider than 256 / 512 floats need 512- / 256-thread CTAs); 0 = unknown */
-    uint32_t seed;         /* reserved */
+    uint32_t hot_min_degree; /* items rated at least this often (at most one per SM) are split off into a "hot"
+                              sub-plan whose chains a whole CTA resolves as exact mini-batches (linear kernel);
+                              0 = default (4096), 0xffffffff = never split */
 } mfk_plan_opts;
 
 typedef struct {
@@ -75,6 +77,9 @@ typedef struct {
     int32_t max_items_per_worker;
     int64_t max_worker_ratings; /* longest worker list (load balance / critical path) */
     int64_t max_item_degree, max_user_degree;
+    int32_t n_hot_items;   /* items in the hot sub-plan (0 = no split) */
+    int32_t reserved;
+    int64_t n_hot_ratings;
 } mfk_plan_info;
 
 /* d_u/d_i/d_r: the n ratings as internal ids (0..n_users-1 / 0..n_items-1).  Synchronises

@@ -33,7 +33,7 @@ def _nvcc() -> str:
 
 
 def _deps():
-    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h"))]
+    out = [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".cu", ".cuh", ".h", ".inc"))]
     out.append(os.path.join(INCLUDE, "mfk.h"))
     out.append(os.path.abspath(__file__))
     return out

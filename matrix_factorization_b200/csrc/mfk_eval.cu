@@ -148,22 +148,34 @@ static int check_factors(const char *who, const float *P, const float *Q, const 
     return MFK_OK;
 }
 
+// One or two rating segments (the second one is the hot sub-plan of a split plan); partial sums of both
+// go to consecutive workspace slots and are added in a fixed order.
 static int run_sse(int kernel, bool bias_only, const int32_t *u, const int32_t *i, const float *r, int64_t n,
-                   const EvalParams &e, void *ws, double *out, cudaStream_t st) {
+                   const EvalParams &e, void *ws, double *out, cudaStream_t st, const int32_t *u2 = nullptr,
+                   const int32_t *i2 = nullptr, const float *r2 = nullptr, int64_t n2 = 0) {
     MFK_REQUIRE(ws && out, "sse: null workspace/output");
     double *partial = reinterpret_cast<double *>(ws);
-    int blocks = eval_blocks(n);
-    if (n == 0) {
+    if (n == 0 && n2 == 0) {
         MFK_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
         return MFK_OK;
     }
-    MFK_REQUIRE(u && i && r, "sse: null rating arrays");
-    if (bias_only) k_sse<MFK_KERNEL_LINEAR, true><<<blocks, kEvalThreads, 0, st>>>(u, i, r, n, e, partial);
-    else if (kernel == MFK_KERNEL_LINEAR) k_sse<MFK_KERNEL_LINEAR, false><<<blocks, kEvalThreads, 0, st>>>(u, i, r, n, e, partial);
-    else if (kernel == MFK_KERNEL_SIGMOID) k_sse<MFK_KERNEL_SIGMOID, false><<<blocks, kEvalThreads, 0, st>>>(u, i, r, n, e, partial);
-    else k_sse<MFK_KERNEL_RBF, false><<<blocks, kEvalThreads, 0, st>>>(u, i, r, n, e, partial);
-    MFK_LAUNCH_CHECK();
-    k_sse_final<<<1, 32, 0, st>>>(partial, blocks, out);
+    int total_blocks = 0;
+    for (int seg = 0; seg < 2; ++seg) {
+        const int32_t *su = seg ? u2 : u, *si = seg ? i2 : i;
+        const float *sr = seg ? r2 : r;
+        const int64_t sn = seg ? n2 : n;
+        if (sn == 0) continue;
+        MFK_REQUIRE(su && si && sr, "sse: null rating arrays");
+        const int blocks = eval_blocks(sn);
+        double *pp = partial + total_blocks;
+        if (bias_only) k_sse<MFK_KERNEL_LINEAR, true><<<blocks, kEvalThreads, 0, st>>>(su, si, sr, sn, e, pp);
+        else if (kernel == MFK_KERNEL_LINEAR) k_sse<MFK_KERNEL_LINEAR, false><<<blocks, kEvalThreads, 0, st>>>(su, si, sr, sn, e, pp);
+        else if (kernel == MFK_KERNEL_SIGMOID) k_sse<MFK_KERNEL_SIGMOID, false><<<blocks, kEvalThreads, 0, st>>>(su, si, sr, sn, e, pp);
+        else k_sse<MFK_KERNEL_RBF, false><<<blocks, kEvalThreads, 0, st>>>(su, si, sr, sn, e, pp);
+        MFK_LAUNCH_CHECK();
+        total_blocks += blocks;
+    }
+    k_sse_final<<<1, 32, 0, st>>>(partial, total_blocks, out);
     MFK_LAUNCH_CHECK();
     return MFK_OK;
 }
@@ -172,7 +184,7 @@ static int run_sse(int kernel, bool bias_only, const int32_t *u, const int32_t *
 
 using namespace mfk;
 
-extern "C" size_t mfk_sse_workspace_bytes(void) { return sizeof(double) * (size_t)kEvalMaxBlocks; }
+extern "C" size_t mfk_sse_workspace_bytes(void) { return sizeof(double) * 2 * (size_t)kEvalMaxBlocks; }
 
 extern "C" int mfk_kmf_sse(int kernel, const int32_t *d_u, const int32_t *d_i, const float *d_r, int64_t n,
                            const float *d_P, const float *d_Q, const float *d_bu, const float *d_bi,
@@ -191,8 +203,16 @@ extern "C" int mfk_kmf_sse_plan(const mfk_plan *plan, int kernel, const float *d
                                 float global_mean, float gamma, float min_rating, float max_rating, void *d_ws,
                                 double *d_sse, void *stream) {
     MFK_REQUIRE(plan != nullptr, "mfk_kmf_sse_plan: plan is NULL");
-    return mfk_kmf_sse(kernel, plan->su, plan->si, plan->sr, plan->n, d_P, d_Q, d_bu, d_bi, n_factors, ld,
-                       global_mean, gamma, min_rating, max_rating, d_ws, d_sse, stream);
+    if (!plan->hot)
+        return mfk_kmf_sse(kernel, plan->su, plan->si, plan->sr, plan->n, d_P, d_Q, d_bu, d_bi, n_factors, ld,
+                           global_mean, gamma, min_rating, max_rating, d_ws, d_sse, stream);
+    MFK_REQUIRE(kernel >= 0 && kernel <= 2, "mfk_kmf_sse_plan: bad kernel %d", kernel);
+    int rc = check_factors("mfk_kmf_sse_plan", d_P, d_Q, d_bu, d_bi, n_factors, ld);
+    if (rc) return rc;
+    EvalParams e{d_P, d_Q, d_bu, d_bi, (n_factors + 3) & ~3, ld, global_mean, gamma, min_rating,
+                 max_rating - min_rating};
+    return run_sse(kernel, false, plan->su, plan->si, plan->sr, plan->n, e, d_ws, d_sse, as_stream(stream),
+                   plan->hot->su, plan->hot->si, plan->hot->sr, plan->hot->n);
 }
 
 extern "C" int mfk_kmf_predict(int kernel, const int32_t *d_u, const int32_t *d_i, int64_t n, const float *d_P,

@@ -291,231 +291,5 @@ extern "C" int mfk_device_query(int device, int *sm_count, int *cc, size_t *smem
     return MFK_OK;
 }
 
-static void plan_free(mfk_plan *p) {
-    if (!p) return;
-    void *ptrs[] = {p->su, p->si, p->sslot, p->sr, p->sstep, p->rec, p->sidx, p->wbeg, p->witems,
-                    p->iworker, p->islot, p->ustripe, p->flags, p->stats};
-    for (void *q : ptrs)
-        if (q) cudaFree(q);
-    delete p;
-}
-
-extern "C" int mfk_plan_destroy(mfk_plan *plan) {
-    plan_free(plan);
-    return MFK_OK;
-}
-
-extern "C" int mfk_plan_create(mfk_plan **out, const int32_t *d_u, const int32_t *d_i, const float *d_r,
-                               int64_t n, int32_t n_users, int32_t n_items, const mfk_plan_opts *opts,
-                               void *stream) {
-    MFK_REQUIRE(out != nullptr, "mfk_plan_create: out is NULL");
-    *out = nullptr;
-    MFK_REQUIRE(n >= 0 && n < (int64_t)INT32_MAX, "mfk_plan_create: n=%lld out of range", (long long)n);
-    MFK_REQUIRE(n_users > 0 && n_items > 0, "mfk_plan_create: n_users/n_items must be positive");
-    MFK_REQUIRE(n == 0 || (d_u && d_i && d_r), "mfk_plan_create: null rating arrays");
-    DeviceProps props;
-    int rc = device_props(&props);
-    if (rc) return rc;
-    cudaStream_t st = as_stream(stream);
-
-    mfk_plan *p = new mfk_plan();
-    p->n = n;
-    p->n_users = n_users;
-    p->n_items = n_items;
-    choose_workers(n, n_users, n_items, props.sm_count, opts, &p->n_ctas, &p->warps_per_cta);
-    p->W = p->n_ctas * p->warps_per_cta;
-    const int32_t W = p->W;
-    if (W >= (1 << (kPlanWorkerShift - kPlanStepShift))) {
-        plan_free(p);
-        set_error("mfk_plan_create: %d workers exceed the key layout", W);
-        return MFK_ERR_UNSUPPORTED;
-    }
-    p->max_slots = (n_items + W - 1) / W;
-    if ((uint64_t)p->max_slots >= (1ull << kPlanStepShift)) {
-        plan_free(p);
-        set_error("mfk_plan_create: %d items per worker exceed the key layout", p->max_slots);
-        return MFK_ERR_UNSUPPORTED;
-    }
-
-#define PLAN_CUDA(call)                                                                       \
-    do {                                                                                      \
-        cudaError_t e__ = (call);                                                             \
-        if (e__ != cudaSuccess) {                                                             \
-            set_error("%s failed at %s:%d: %s", #call, __FILE__, __LINE__, cudaGetErrorString(e__)); \
-            plan_free(p);                                                                     \
-            for (void *q : scratch) cudaFree(q);                                              \
-            return MFK_ERR_CUDA;                                                              \
-        }                                                                                     \
-    } while (0)
-    std::vector<void *> scratch;
-    auto dalloc = [&](void **ptr, size_t bytes) { return cudaMalloc(ptr, bytes ? bytes : 16); };
-
-    size_t nn = (size_t)std::max<int64_t>(n, 1);
-    PLAN_CUDA(dalloc((void **)&p->su, nn * 4));
-    PLAN_CUDA(dalloc((void **)&p->si, nn * 4));
-    PLAN_CUDA(dalloc((void **)&p->sslot, nn * 4));
-    PLAN_CUDA(dalloc((void **)&p->sr, nn * 4));
-    PLAN_CUDA(dalloc((void **)&p->sstep, nn * 4));
-    PLAN_CUDA(dalloc((void **)&p->rec, nn * 16));
-    PLAN_CUDA(dalloc((void **)&p->sidx, nn * 4));
-    PLAN_CUDA(dalloc((void **)&p->wbeg, sizeof(int64_t) * (size_t)(W + 1)));
-    PLAN_CUDA(dalloc((void **)&p->witems, sizeof(int32_t) * (size_t)p->max_slots * W));
-    PLAN_CUDA(dalloc((void **)&p->iworker, sizeof(int32_t) * (size_t)n_items));
-    PLAN_CUDA(dalloc((void **)&p->islot, sizeof(int32_t) * (size_t)n_items));
-    PLAN_CUDA(dalloc((void **)&p->ustripe, sizeof(int32_t) * (size_t)n_users));
-    PLAN_CUDA(dalloc((void **)&p->flags, sizeof(int32_t) * (size_t)(W + 32)));
-    PLAN_CUDA(cudaMemsetAsync(p->flags, 0, sizeof(int32_t) * (size_t)(W + 32), st));
-    PLAN_CUDA(dalloc((void **)&p->stats, sizeof(long long) * 12 * (size_t)W));
-    PLAN_CUDA(cudaMemsetAsync(p->stats, 0, sizeof(long long) * 12 * (size_t)W, st));
-    PLAN_CUDA(cudaMemsetAsync(p->witems, 0xff, sizeof(int32_t) * (size_t)p->max_slots * W, st));
-
-    int32_t *deg_u = nullptr, *deg_i = nullptr, *sorted_u = nullptr, *sorted_i = nullptr, *bad = nullptr;
-    PLAN_CUDA(dalloc((void **)&deg_u, sizeof(int32_t) * (size_t)n_users)); scratch.push_back(deg_u);
-    PLAN_CUDA(dalloc((void **)&deg_i, sizeof(int32_t) * (size_t)n_items)); scratch.push_back(deg_i);
-    PLAN_CUDA(dalloc((void **)&sorted_u, sizeof(int32_t) * (size_t)n_users)); scratch.push_back(sorted_u);
-    PLAN_CUDA(dalloc((void **)&sorted_i, sizeof(int32_t) * (size_t)n_items)); scratch.push_back(sorted_i);
-    PLAN_CUDA(dalloc((void **)&bad, sizeof(int32_t))); scratch.push_back(bad);
-    PLAN_CUDA(cudaMemsetAsync(deg_u, 0, sizeof(int32_t) * (size_t)n_users, st));
-    PLAN_CUDA(cudaMemsetAsync(deg_i, 0, sizeof(int32_t) * (size_t)n_items, st));
-    PLAN_CUDA(cudaMemsetAsync(bad, 0, sizeof(int32_t), st));
-    if (n > 0) {
-        k_degrees<<<grid_for(n), 256, 0, st>>>(d_u, d_i, n, n_users, n_items, deg_u, deg_i, bad);
-        PLAN_CUDA(cudaGetLastError());
-    }
-    int32_t h_bad = 0;
-    PLAN_CUDA(cudaMemcpyAsync(&h_bad, bad, sizeof(int32_t), cudaMemcpyDeviceToHost, st));
-    PLAN_CUDA(cudaStreamSynchronize(st));
-    if (h_bad != 0) {
-        plan_free(p);
-        for (void *q : scratch) cudaFree(q);
-        set_error("mfk_plan_create: %d ratings have ids outside [0,n_users) x [0,n_items)", h_bad);
-        return MFK_ERR_ARG;
-    }
-    rc = sort_by_degree(deg_u, n_users, sorted_u, st);
-    if (rc == MFK_OK) rc = sort_by_degree(deg_i, n_items, sorted_i, st);
-    if (rc != MFK_OK) {
-        plan_free(p);
-        for (void *q : scratch) cudaFree(q);
-        return rc;
-    }
-    k_deal<<<(n_users + 255) / 256, 256, 0, st>>>(sorted_u, n_users, W, 0, 0, p->ustripe, nullptr, nullptr);
-    PLAN_CUDA(cudaGetLastError());
-    k_deal<<<(n_items + 255) / 256, 256, 0, st>>>(sorted_i, n_items, W, p->n_ctas, p->warps_per_cta, p->iworker,
-                                                    p->islot, p->witems);
-    PLAN_CUDA(cudaGetLastError());
-    {   // degree extremes for the info struct
-        int32_t top_u = 0, top_i = 0, hu = 0, hi = 0;
-        PLAN_CUDA(cudaMemcpyAsync(&top_u, sorted_u, 4, cudaMemcpyDeviceToHost, st));
-        PLAN_CUDA(cudaMemcpyAsync(&top_i, sorted_i, 4, cudaMemcpyDeviceToHost, st));
-        PLAN_CUDA(cudaStreamSynchronize(st));
-        PLAN_CUDA(cudaMemcpyAsync(&hu, deg_u + top_u, 4, cudaMemcpyDeviceToHost, st));
-        PLAN_CUDA(cudaMemcpyAsync(&hi, deg_i + top_i, 4, cudaMemcpyDeviceToHost, st));
-        PLAN_CUDA(cudaStreamSynchronize(st));
-        p->max_user_degree = hu;
-        p->max_item_degree = hi;
-    }
-
-    if (n > 0) {
-        uint64_t *keys_a = nullptr, *keys_b = nullptr;
-        int32_t *idx_a = nullptr;
-        void *tmp = nullptr;
-        size_t tmp_bytes = 0;
-        PLAN_CUDA(dalloc((void **)&keys_a, nn * 8)); scratch.push_back(keys_a);
-        PLAN_CUDA(dalloc((void **)&keys_b, nn * 8)); scratch.push_back(keys_b);
-        PLAN_CUDA(dalloc((void **)&idx_a, nn * 4)); scratch.push_back(idx_a);
-        k_keys<<<grid_for(n), 256, 0, st>>>(d_u, d_i, n, p->ustripe, p->iworker, p->islot, W, keys_a, idx_a);
-        PLAN_CUDA(cudaGetLastError());
-        int end_bit = std::min(64, kPlanWorkerShift + bits_for((uint64_t)W));
-        PLAN_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, keys_a, keys_b, idx_a, p->sidx, (int)n, 0,
-                                                  end_bit, st));
-        PLAN_CUDA(dalloc(&tmp, tmp_bytes)); scratch.push_back(tmp);
-        PLAN_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, keys_a, keys_b, idx_a, p->sidx, (int)n, 0,
-                                                  end_bit, st));
-        k_gather<<<grid_for(n), 256, 0, st>>>(keys_b, p->sidx, n, d_u, d_i, d_r, p->su, p->si, p->sslot,
-                                               p->sr, p->sstep);
-        PLAN_CUDA(cudaGetLastError());
-        k_build_records<<<grid_for(n), 256, 0, st>>>(keys_b, p->su, p->sr, n, n_users, p->rec);
-        PLAN_CUDA(cudaGetLastError());
-        k_worker_bounds<<<(W + 1 + 255) / 256, 256, 0, st>>>(keys_b, n, W, p->wbeg);
-        PLAN_CUDA(cudaGetLastError());
-    } else {
-        PLAN_CUDA(cudaMemsetAsync(p->wbeg, 0, sizeof(int64_t) * (size_t)(W + 1), st));
-    }
-    {
-        std::vector<int64_t> h_wbeg((size_t)W + 1);
-        PLAN_CUDA(cudaMemcpyAsync(h_wbeg.data(), p->wbeg, sizeof(int64_t) * (size_t)(W + 1),
-                                  cudaMemcpyDeviceToHost, st));
-        PLAN_CUDA(cudaStreamSynchronize(st));
-        int64_t mx = 0;
-        for (int32_t w = 0; w < W; ++w) mx = std::max(mx, h_wbeg[w + 1] - h_wbeg[w]);
-        p->max_worker_ratings = mx;
-    }
-    for (void *q : scratch) cudaFree(q);
-    scratch.clear();
-#undef PLAN_CUDA
-    p->epoch = 0;
-    *out = p;
-    return MFK_OK;
-}
-
-extern "C" int mfk_plan_get_info(const mfk_plan *plan, mfk_plan_info *info) {
-    MFK_REQUIRE(plan && info, "mfk_plan_get_info: null argument");
-    info->n = plan->n;
-    info->n_users = plan->n_users;
-    info->n_items = plan->n_items;
-    info->n_workers = plan->W;
-    info->n_ctas = plan->n_ctas;
-    info->warps_per_cta = plan->warps_per_cta;
-    info->max_items_per_worker = plan->max_slots;
-    info->max_worker_ratings = plan->max_worker_ratings;
-    info->max_item_degree = plan->max_item_degree;
-    info->max_user_degree = plan->max_user_degree;
-    return MFK_OK;
-}
-
-extern "C" int mfk_plan_order(const mfk_plan *plan, int64_t *d_order, void *stream) {
-    MFK_REQUIRE(plan && (d_order || plan->n == 0), "mfk_plan_order: null argument");
-    if (plan->n == 0) return MFK_OK;
-    cudaStream_t st = as_stream(stream);
-    const int64_t n = plan->n;
-    int32_t *pos_in = nullptr, *pos_out = nullptr, *step_out = nullptr;
-    void *tmp = nullptr;
-    size_t tmp_bytes = 0;
-    MFK_CUDA(cudaMalloc(&pos_in, (size_t)n * 4));
-    MFK_CUDA(cudaMalloc(&pos_out, (size_t)n * 4));
-    MFK_CUDA(cudaMalloc(&step_out, (size_t)n * 4));
-    k_pos_iota<<<grid_for(n), 256, 0, st>>>(pos_in, n);
-    MFK_LAUNCH_CHECK();
-    int end_bit = bits_for((uint64_t)plan->W);
-    // stable sort by step: positions are worker-major already, so the result is
-    // (step, worker, in-block position) -- every step is one conflict-free wave.
-    MFK_CUDA(cub::DeviceRadixSort::SortPairs(nullptr, tmp_bytes, plan->sstep, step_out, pos_in, pos_out, (int)n, 0,
-                                             end_bit, st));
-    MFK_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 16));
-    MFK_CUDA(cub::DeviceRadixSort::SortPairs(tmp, tmp_bytes, plan->sstep, step_out, pos_in, pos_out, (int)n, 0,
-                                             end_bit, st));
-    k_order_out<<<grid_for(n), 256, 0, st>>>(pos_out, plan->sidx, n, d_order);
-    MFK_LAUNCH_CHECK();
-    MFK_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp);
-    cudaFree(pos_in);
-    cudaFree(pos_out);
-    cudaFree(step_out);
-    return MFK_OK;
-}
-
-extern "C" int mfk_plan_stats(const mfk_plan *plan, int64_t *d_stats, void *stream) {
-    MFK_REQUIRE(plan && d_stats, "mfk_plan_stats: null argument");
-    MFK_CUDA(cudaMemcpyAsync(d_stats, plan->stats, sizeof(long long) * 12 * (size_t)plan->W, cudaMemcpyDeviceToDevice,
-                             as_stream(stream)));
-    return MFK_OK;
-}
-
-extern "C" int mfk_plan_assignment(const mfk_plan *plan, int32_t *d_worker, int32_t *d_step, void *stream) {
-    MFK_REQUIRE(plan && ((d_worker && d_step) || plan->n == 0), "mfk_plan_assignment: null argument");
-    if (plan->n == 0) return MFK_OK;
-    k_assignment<<<grid_for(plan->n), 256, 0, as_stream(stream)>>>(plan->wbeg, plan->W, plan->sidx, plan->sstep,
-                                                                  plan->n, d_worker, d_step);
-    MFK_LAUNCH_CHECK();
-    return MFK_OK;
-}
+// The C-ABI entry points of the plan (create / destroy / info / order / assignment / stats).
+#include "mfk_plan_api.inc"

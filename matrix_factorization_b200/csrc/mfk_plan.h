@@ -34,6 +34,11 @@ struct mfk_plan {
     int32_t *iworker = nullptr, *islot = nullptr;  // per item
     int32_t *ustripe = nullptr;                    // per user
     int32_t *flags = nullptr;  // [W] ring progress flags (monotone across epochs)
+    // hot/cold split (optional): `hot` is a plan over the ratings of the most-rated items (one item per
+    // worker, worker = one CTA); this plan then covers the remaining ratings.  n_total counts both.
+    mfk_plan *hot = nullptr;
+    int64_t n_total = 0;
+    int32_t n_hot_items = 0;
     long long *stats = nullptr;  // [W][4] per-worker counters of the last SGD epoch (diagnostics)
     int64_t epoch = 0;         // epochs run so far (flag base = epoch * (W + 1))
 };

@@ -665,6 +665,8 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
     }
 }
 
+#include "mfk_sgd_hot.inc"
+
 template <int KERNEL, int NV, bool QSMEM>
 static int launch_ring(const mfk_plan *plan, const SgdParams &prm, int depth, size_t smem, cudaStream_t st) {
     RingView rv;
@@ -775,7 +777,7 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         set_error("mfk_kmf_sgd_epoch: n_factors=%d > %d unsupported", n_factors, MFK_MAX_FACTORS);
         return MFK_ERR_UNSUPPORTED;
     }
-    if (plan->n == 0) return MFK_OK;
+    if (plan->n_total == 0) return MFK_OK;
     cudaStream_t st = as_stream(stream);
     SgdParams prm;
     prm.P = d_P;
@@ -794,6 +796,21 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
     prm.upd_user = update_user_params ? 1 : 0;
     prm.upd_item = update_item_params ? 1 : 0;
     int rc;
+    if (plan->hot && plan->hot->n > 0) {
+        // hot phase first: the most-rated items, one CTA each (exact mini-batches for the linear kernel; the
+        // other kernels walk the same sub-plan with the ring kernel, one warp per item)
+        mfk_plan *hot = plan->hot;
+        SgdParams hp = prm;
+        hp.base = next_base(hot, st, &rc);
+        if (rc) return rc;
+        if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128) rc = launch_hot<1>(hot, hp, st);
+        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256) rc = launch_hot<2>(hot, hp, st);
+        else if (kernel == MFK_KERNEL_LINEAR) rc = launch_ring_nv<MFK_KERNEL_LINEAR>(hot, hp, st);
+        else if (kernel == MFK_KERNEL_SIGMOID) rc = launch_ring_nv<MFK_KERNEL_SIGMOID>(hot, hp, st);
+        else rc = launch_ring_nv<MFK_KERNEL_RBF>(hot, hp, st);
+        if (rc) return rc;
+    }
+    if (plan->n == 0) return MFK_OK;
     prm.base = next_base(plan, st, &rc);
     if (rc) return rc;
     if (kernel == MFK_KERNEL_LINEAR) return launch_ring_nv<MFK_KERNEL_LINEAR>(plan, prm, st);
@@ -806,7 +823,7 @@ extern "C" int mfk_bias_sgd_epoch(mfk_plan *plan, float *d_bu, float *d_bi, floa
     MFK_REQUIRE(plan != nullptr, "mfk_bias_sgd_epoch: plan is NULL");
     MFK_REQUIRE(d_bu && d_bi, "mfk_bias_sgd_epoch: null parameter array");
     MFK_REQUIRE(((uintptr_t)d_bu & 15) == 0, "mfk_bias_sgd_epoch: bu must be 16-byte aligned");
-    if (plan->n == 0) return MFK_OK;
+    if (plan->n_total == 0) return MFK_OK;
     cudaStream_t st = as_stream(stream);
     SgdParams prm;
     prm.P = nullptr;
@@ -825,6 +842,14 @@ extern "C" int mfk_bias_sgd_epoch(mfk_plan *plan, float *d_bu, float *d_bi, floa
     prm.upd_user = update_user_params ? 1 : 0;
     prm.upd_item = update_item_params ? 1 : 0;
     int rc;
+    if (plan->hot && plan->hot->n > 0) {
+        SgdParams hp = prm;
+        hp.base = next_base(plan->hot, st, &rc);
+        if (rc) return rc;
+        rc = launch_ring_q<MFK_KERNEL_LINEAR, 0>(plan->hot, hp, st);
+        if (rc) return rc;
+    }
+    if (plan->n == 0) return MFK_OK;
     prm.base = next_base(plan, st, &rc);
     if (rc) return rc;
     return launch_ring_q<MFK_KERNEL_LINEAR, 0>(plan, prm, st);

@@ -64,13 +64,15 @@ def download(t, dtype=np.float64, cols: int | None = None) -> np.ndarray:
 class Plan:
     """Owner of an mfk_plan handle (stratified conflict-free SGD schedule)."""
 
+    NO_HOT_SPLIT = 0xFFFFFFFF
+
     def __init__(self, u, i, r, n_users: int, n_items: int, n_factors: int = 0, n_workers: int = 0,
-                 warps_per_cta: int = 0):
+                 warps_per_cta: int = 0, hot_min_degree: int = NO_HOT_SPLIT):
         torch = _torch()
         assert u.dtype == torch.int32 and i.dtype == torch.int32 and r.dtype == torch.float32
         self._h = C.c_void_p()
         self.n = int(u.numel())
-        opts = PlanOpts(int(n_workers), int(warps_per_cta), int(n_factors), 0)
+        opts = PlanOpts(int(n_workers), int(warps_per_cta), int(n_factors), int(hot_min_degree))
         check(lib().mfk_plan_create(C.byref(self._h), ptr(u), ptr(i), ptr(r), self.n, int(n_users), int(n_items),
                                     C.byref(opts), stream_ptr()))
 

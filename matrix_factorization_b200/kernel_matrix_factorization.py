@@ -294,8 +294,12 @@ def _sgd(
     du, di, dr = _upload_ratings(u, i, r)
     P, Q = _mirror.rows(user_features), _mirror.rows(item_features)
     bu, bi = _mirror.vec(user_biases), _mirror.vec(item_biases)
-    plan = engine.Plan(du, di, dr, user_features.shape[0], item_features.shape[0], n_factors=F,
-                       **(plan_options or {}))
+    opts = dict(plan_options or {})
+    if "hot_min_degree" not in opts:
+        # the exact mini-batch path for the most-rated items exists for the linear kernel with item updates
+        opts["hot_min_degree"] = 0 if (kernel == "linear" and update_item_params and "n_workers" not in opts) \
+            else engine.Plan.NO_HOT_SPLIT
+    plan = engine.Plan(du, di, dr, user_features.shape[0], item_features.shape[0], n_factors=F, **opts)
     order = plan.order().cpu().numpy() if return_order else None
     sse = torch.zeros((max(n_epochs, 1),), dtype=torch.float64, device=engine.device())
     train_rmse = []

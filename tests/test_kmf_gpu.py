@@ -275,3 +275,58 @@ def test_recommend_matches_reference_lists(golden_dir):
         same = [a == b for a, b in zip(got_items, ref_items)]
         assert rec.index.tolist() == ref["index"] or not all(same)
         assert rec.user_id.tolist() == [int(uid)] * 10
+
+
+@pytest.mark.parametrize("F,U,I,N,hot,min_deg", [
+    (128, 900, 300, 40_000, 0.5, 200),    # several hot items, full 512-byte rows, batches of 64 + ragged tails
+    (100, 600, 200, 20_000, 0.4, 100),    # n_factors % 128 != 0
+    (256, 400, 150, 12_000, 0.4, 150),    # NV = 2
+    (32, 300, 100, 6_000, 0.3, 64),
+])
+def test_hot_item_minibatch_path_matches_replay(F, U, I, N, hot, min_deg):
+    """Hot/cold split plan: the most-rated items are resolved by the CTA-cooperative exact mini-batch kernel
+    (Gram matrix + forward substitution); the emitted order (hot phase, then cold phase) replays to the same
+    factors through the sequential fp64 oracle."""
+    import torch
+    from matrix_factorization_b200 import engine
+    kmf, orc = _mods()
+    rng = np.random.default_rng(F + N)
+    # a handful of very popular items on top of a uniform background
+    n_hot_items = 5
+    keys = rng.choice(U * I, N, replace=False)
+    u, i = (keys // I).astype(np.int64), (keys % I).astype(np.int64)
+    m = rng.random(len(u)) < hot
+    i[m] = rng.integers(0, n_hot_items, m.sum())
+    keep = np.unique(u * I + i, return_index=True)[1]
+    u, i = u[keep], i[keep]
+    r = rng.integers(1, 6, len(u)).astype(np.float64)
+    P, Q = rng.normal(0, 0.1, (U, F)), rng.normal(0, 0.1, (I, F))
+    bu, bi = rng.normal(0, 0.05, U), rng.normal(0, 0.05, I)
+    P0, Q0, bu0, bi0 = P.copy(), Q.copy(), bu.copy(), bi.copy()
+    mu, lr, reg = float(r.mean()), 0.01, 0.02
+    # the plan really is split, and every wave (hot steps first, then cold steps) is conflict-free
+    plan = engine.Plan(torch.tensor(u, dtype=torch.int32).cuda(), torch.tensor(i, dtype=torch.int32).cuda(),
+                       torch.tensor(r, dtype=torch.float32).cuda(), U, I, n_factors=F, hot_min_degree=min_deg)
+    info = plan.info()
+    assert info["n_hot_items"] >= n_hot_items - 1 and info["n_hot_ratings"] > 0 and info["n"] == len(u)
+    w, s = (t.cpu().numpy().astype(np.int64) for t in plan.assignment())
+    order = plan.order().cpu().numpy()
+    assert np.array_equal(np.sort(order), np.arange(len(u))) and np.all(np.diff(s[order]) >= 0)
+    for ids in (u, i):
+        key = s * (ids.max() + 1) + ids
+        srt = np.argsort(key, kind="stable")
+        same = key[srt][1:] == key[srt][:-1]
+        assert np.all(w[srt][1:][same] == w[srt][:-1][same])
+    plan.close()
+    for uu, ui in [(True, True), (True, False)]:
+        Pa, Qa, bua, bia = P0.copy(), Q0.copy(), bu0.copy(), bi0.copy()
+        *_, rm, order = kmf._sgd((u, i, r), mu, bua, bia, Pa, Qa, 2, "linear", 0.01, lr, reg, 0.0, 5.0, 0, uu, ui,
+                                 plan_options=dict(hot_min_degree=min_deg), return_order=True)
+        Po, Qo, buo, bio = P0, Q0, bu0, bi0
+        for e in range(2):
+            Po, Qo, buo, bio = orc.kmf_replay("linear", u, i, r, order, mu, buo, bio, Po, Qo, lr, reg, 0.01, 0.0, 5.0, uu, ui)
+            assert abs(rm[e] - orc.kmf_rmse("linear", u, i, r, mu, buo, bio, Po, Qo)) < 2e-5
+        assert _rel(Pa, Po) < 1e-4 and _rel(Qa, Qo) < 1e-4, (_rel(Pa, Po), _rel(Qa, Qo))
+        assert np.max(np.abs(bua - buo)) < 2e-5 and np.max(np.abs(bia - bio)) < 2e-5
+        if not ui:
+            assert np.array_equal(Qa, Q0) and np.array_equal(bia, bi0)

@@ -22,6 +22,7 @@ def main():
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--epochs", type=int, default=3)
     ap.add_argument("--tag", default="")
+    ap.add_argument("--no-hot", action="store_true")
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     wl = bench.gen_workload(args.workload, dev, uniform=args.uniform)
@@ -31,9 +32,12 @@ def main():
     Q = torch.randn(I, F, device=dev, generator=g) * 0.1
     bu, bi = torch.zeros(U, device=dev), torch.zeros(I, device=dev)
     mu = float(wl["r"].double().mean().item())
-    plan = engine.Plan(wl["u"], wl["i"], wl["r"], U, I, n_factors=F, n_workers=args.workers, warps_per_cta=args.warps)
+    plan = engine.Plan(wl["u"], wl["i"], wl["r"], U, I, n_factors=F, n_workers=args.workers, warps_per_cta=args.warps,
+                       hot_min_degree=engine.Plan.NO_HOT_SPLIT if args.no_hot else 0)
     info = plan.info()
     w, s = plan.assignment()
+    H = info["n_hot_items"]
+    w, s = w[w >= H] - H, s[w >= H] - H  # cold workers only (hot workers / steps are numbered first)
     counts = torch.bincount(w.long(), minlength=info["n_workers"]).cpu().numpy()
     steps_nonempty = torch.unique(w.long() * 65536 + s.long()).div(65536, rounding_mode="floor").bincount(minlength=info["n_workers"]).cpu().numpy()
     ms = []
