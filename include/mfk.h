@@ -97,7 +97,8 @@ int mfk_plan_order(const mfk_plan *plan, int64_t *d_order, void *stream);
  * that each (step) wave is conflict-free. */
 int mfk_plan_assignment(const mfk_plan *plan, int32_t *d_worker, int32_t *d_step, void *stream);
 
-/* Diagnostics of the last SGD epoch run on the plan: d_stats is int64[12 * n_workers] (device):
+/* Diagnostics of the last SGD epoch run on the plan: d_stats is int64[12 * (n_workers + n_hot_items)] (device;
+ * the hot sub-plan's block of 12 * n_hot_items values follows the main block in the same layout):
  * first [n_workers][4] = {SM cycles from start to last rating, cycles blocked in ring hand-off
  * waits, 4-rating chains resolved at once, ratings processed singly}, then [n_workers][8] phase
  * cycle counters that only builds with -DMFK_RING_PROFILE=1 fill in. */

@@ -102,11 +102,15 @@ class Plan:
     def stats(self):
         """[n_workers, 4] int64 host array: cycles, blocked cycles, 4-chains, singles of the last epoch."""
         torch = _torch()
-        W = self.info()["n_workers"]
-        out = torch.empty((12 * W,), dtype=torch.int64, device=device())
+        info = self.info()
+        W, H = info["n_workers"], info["n_hot_items"]
+        out = torch.zeros((12 * (W + H),), dtype=torch.int64, device=device())
         check(lib().mfk_plan_stats(self._h, ptr(out), stream_ptr()))
         out = out.cpu().numpy()
-        self.last_profile = out[4 * W:].reshape(W, 8)  # phase counters (MFK_RING_PROFILE builds only)
+        self.last_profile = out[4 * W:12 * W].reshape(W, 8)  # phase counters (MFK_RING_PROFILE builds only)
+        hot = out[12 * W:]
+        self.hot_stats = hot[:4 * H].reshape(H, 4)    # cycles, blocked cycles, batches, ratings per hot item
+        self.hot_profile = hot[4 * H:].reshape(H, 8)  # phase cycles of the hot kernel
         return out[:4 * W].reshape(W, 4)
 
     def close(self):

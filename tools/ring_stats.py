@@ -67,6 +67,15 @@ def main():
     print("median worker:", med, counts[med], steps_nonempty[med], st[med, 0] / 1e6, st[med, 1] / 1e6, busy[med] / max(1, counts[med]), st[med, 2], st[med, 3])
     print("busy cycles/rating percentiles (all workers):", np.percentile(busy / np.maximum(1, counts), [5, 50, 95]))
     print("sum busy Mcyc", busy.sum() / 1e6, "max total Mcyc", st[:, 0].max() / 1e6)
+    if H:
+        hs, hp = plan.hot_stats, plan.hot_profile
+        top = np.argsort(-hs[:, 3])[:3]
+        print("hot items:", H, "max cycles (M)", hs[:, 0].max() / 1e6, "ratings max", hs[:, 3].max())
+        names = ["handoff", "rowload", "gram", "subst", "sweep", "misc"]
+        for x in top:
+            print("hot worker", x, "ratings", hs[x, 3], "batches", hs[x, 2], "Mcyc", hs[x, 0] / 1e6, "blocked", hs[x, 1] / 1e6,
+                  {n: round(float(v) / 1e6, 2) for n, v in zip(names, hp[x])},
+                  "cyc/batch", {n: int(v / max(1, hs[x, 2])) for n, v in zip(names, hp[x])})
 
 
 if __name__ == "__main__":
