@@ -53,9 +53,9 @@ int mfk_device_query(int device, int *sm_count, int *cc, size_t *smem_optin);
  *
  * Replaces the per-epoch `np.random.shuffle(X)` + sequential rating loop of
  * kernel_matrix_factorization.py:369-425 and baseline_model.py:250-266 by a static DSGD
- * schedule: items are dealt to W worker warps (nnz-balanced), users to W stripes; at step s
- * worker w owns user stripe (w + s) mod W, so no two ratings in flight share a user or an
- * item.  The plan holds the ratings re-ordered per worker (step-major, item-minor).
+ * schedule: items are dealt to W worker warps (nnz-balanced), users to R = c * W stripes; at
+ * step s worker w owns user stripe (c * w + s) mod R and may enter it once worker w + 1 has
+ * finished its step s - c, so no two ratings in flight share a user or an item.  The plan holds the ratings re-ordered per worker (step-major, item-minor).
  * ---------------------------------------------------------------------------------- */
 typedef struct mfk_plan mfk_plan;
 
@@ -67,19 +67,30 @@ typedef struct {
     uint32_t hot_min_degree; /* items rated at least this often (at most one per SM) are split off into a "hot"
                               sub-plan whose chains a whole CTA resolves as exact mini-batches (linear kernel);
                               0 = default (4096), 0xffffffff = never split */
+    uint32_t stripe_slack; /* user stripes per worker (steps per epoch = stripe_slack * n_workers): step s of a
+                              worker needs step s - stripe_slack of its ring neighbour, so a worker may run
+                              stripe_slack - 1 steps ahead of the hand-off; 0 = default */
+    uint32_t schedule;     /* how the workers synchronise: 0 = default (1), 1 = dataflow -- every rating waits for
+                              exactly the previous rating of its user (per-user version counters), 2 = ring --
+                              workers hand whole user stripes around in lockstep */
+    uint32_t no_hot_users; /* 1 = split off hot items only (by default the most active users among the remaining
+                              ratings get the same treatment, with the roles of users and items exchanged) */
 } mfk_plan_opts;
 
 typedef struct {
     int64_t n;
     int32_t n_users, n_items;
-    int32_t n_workers;     /* W: worker warps == user stripes == steps per epoch */
+    int32_t n_workers;     /* W: worker warps */
     int32_t n_ctas, warps_per_cta;
     int32_t max_items_per_worker;
     int64_t max_worker_ratings; /* longest worker list (load balance / critical path) */
     int64_t max_item_degree, max_user_degree;
     int32_t n_hot_items;   /* items in the hot sub-plan (0 = no split) */
-    int32_t reserved;
+    int32_t n_steps;       /* R: user stripes == steps per epoch (stripe_slack * n_workers) */
     int64_t n_hot_ratings;
+    int32_t n_hot_users;   /* users in the hot-user sub-plan */
+    int32_t reserved;
+    int64_t n_hot_user_ratings;
 } mfk_plan_info;
 
 /* d_u/d_i/d_r: the n ratings as internal ids (0..n_users-1 / 0..n_items-1).  Synchronises
@@ -97,8 +108,8 @@ int mfk_plan_order(const mfk_plan *plan, int64_t *d_order, void *stream);
  * that each (step) wave is conflict-free. */
 int mfk_plan_assignment(const mfk_plan *plan, int32_t *d_worker, int32_t *d_step, void *stream);
 
-/* Diagnostics of the last SGD epoch run on the plan: d_stats is int64[12 * (n_workers + n_hot_items)] (device;
- * the hot sub-plan's block of 12 * n_hot_items values follows the main block in the same layout):
+/* Diagnostics of the last SGD epoch run on the plan: d_stats is int64[12 * (n_workers + n_hot_items +
+ * n_hot_users)] (device; the blocks of the hot-item and the hot-user sub-plan follow the main block, same layout):
  * first [n_workers][4] = {SM cycles from start to last rating, cycles blocked in ring hand-off
  * waits, 4-rating chains resolved at once, ratings processed singly}, then [n_workers][8] phase
  * cycle counters that only builds with -DMFK_RING_PROFILE=1 fill in. */

@@ -24,14 +24,15 @@ class MfkError(RuntimeError):
 
 class PlanOpts(C.Structure):
     _fields_ = [("n_workers", C.c_int32), ("warps_per_cta", C.c_int32), ("n_factors", C.c_int32),
-                ("hot_min_degree", C.c_uint32)]
+                ("hot_min_degree", C.c_uint32), ("stripe_slack", C.c_uint32), ("schedule", C.c_uint32), ("no_hot_users", C.c_uint32)]
 
 
 class PlanInfo(C.Structure):
     _fields_ = [("n", C.c_int64), ("n_users", C.c_int32), ("n_items", C.c_int32), ("n_workers", C.c_int32),
                 ("n_ctas", C.c_int32), ("warps_per_cta", C.c_int32), ("max_items_per_worker", C.c_int32),
                 ("max_worker_ratings", C.c_int64), ("max_item_degree", C.c_int64), ("max_user_degree", C.c_int64),
-                ("n_hot_items", C.c_int32), ("reserved", C.c_int32), ("n_hot_ratings", C.c_int64)]
+                ("n_hot_items", C.c_int32), ("n_steps", C.c_int32), ("n_hot_ratings", C.c_int64),
+                ("n_hot_users", C.c_int32), ("reserved", C.c_int32), ("n_hot_user_ratings", C.c_int64)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

@@ -148,22 +148,31 @@ static int check_factors(const char *who, const float *P, const float *Q, const 
     return MFK_OK;
 }
 
-// One or two rating segments (the second one is the hot sub-plan of a split plan); partial sums of both
-// go to consecutive workspace slots and are added in a fixed order.
-static int run_sse(int kernel, bool bias_only, const int32_t *u, const int32_t *i, const float *r, int64_t n,
-                   const EvalParams &e, void *ws, double *out, cudaStream_t st, const int32_t *u2 = nullptr,
-                   const int32_t *i2 = nullptr, const float *r2 = nullptr, int64_t n2 = 0) {
+struct RatingSeg {
+    const int32_t *u, *i;
+    const float *r;
+    int64_t n;
+};
+
+// Up to kMaxSegs rating segments (the phases of a split plan); the partial sums go to consecutive workspace
+// slots and are added in a fixed order.
+constexpr int kMaxSegs = 3;
+static int run_sse(int kernel, bool bias_only, const RatingSeg *segs, int n_segs, const EvalParams &e, void *ws,
+                   double *out, cudaStream_t st) {
     MFK_REQUIRE(ws && out, "sse: null workspace/output");
+    MFK_REQUIRE(n_segs <= kMaxSegs, "sse: too many segments");
     double *partial = reinterpret_cast<double *>(ws);
-    if (n == 0 && n2 == 0) {
+    int64_t n_all = 0;
+    for (int seg = 0; seg < n_segs; ++seg) n_all += segs[seg].n;
+    if (n_all == 0) {
         MFK_CUDA(cudaMemsetAsync(out, 0, sizeof(double), st));
         return MFK_OK;
     }
     int total_blocks = 0;
-    for (int seg = 0; seg < 2; ++seg) {
-        const int32_t *su = seg ? u2 : u, *si = seg ? i2 : i;
-        const float *sr = seg ? r2 : r;
-        const int64_t sn = seg ? n2 : n;
+    for (int seg = 0; seg < n_segs; ++seg) {
+        const int32_t *su = segs[seg].u, *si = segs[seg].i;
+        const float *sr = segs[seg].r;
+        const int64_t sn = segs[seg].n;
         if (sn == 0) continue;
         MFK_REQUIRE(su && si && sr, "sse: null rating arrays");
         const int blocks = eval_blocks(sn);
@@ -184,7 +193,7 @@ static int run_sse(int kernel, bool bias_only, const int32_t *u, const int32_t *
 
 using namespace mfk;
 
-extern "C" size_t mfk_sse_workspace_bytes(void) { return sizeof(double) * 2 * (size_t)kEvalMaxBlocks; }
+extern "C" size_t mfk_sse_workspace_bytes(void) { return sizeof(double) * kMaxSegs * (size_t)kEvalMaxBlocks; }
 
 extern "C" int mfk_kmf_sse(int kernel, const int32_t *d_u, const int32_t *d_i, const float *d_r, int64_t n,
                            const float *d_P, const float *d_Q, const float *d_bu, const float *d_bi,
@@ -195,7 +204,17 @@ extern "C" int mfk_kmf_sse(int kernel, const int32_t *d_u, const int32_t *d_i, c
     if (rc) return rc;
     EvalParams e{d_P, d_Q, d_bu, d_bi, (n_factors + 3) & ~3, ld, global_mean, gamma, min_rating,
                  max_rating - min_rating};
-    return run_sse(kernel, false, d_u, d_i, d_r, n, e, d_ws, d_sse, as_stream(stream));
+    const RatingSeg seg{d_u, d_i, d_r, n};
+    return run_sse(kernel, false, &seg, 1, e, d_ws, d_sse, as_stream(stream));
+}
+
+// the rating segments of a plan: cold part, hot items, hot users (whose arrays hold the roles exchanged)
+static int plan_segments(const mfk_plan *plan, RatingSeg *segs) {
+    int k = 0;
+    segs[k++] = RatingSeg{plan->su, plan->si, plan->sr, plan->n};
+    if (plan->hot) segs[k++] = RatingSeg{plan->hot->su, plan->hot->si, plan->hot->sr, plan->hot->n};
+    if (plan->hot_users) segs[k++] = RatingSeg{plan->hot_users->si, plan->hot_users->su, plan->hot_users->sr, plan->hot_users->n};
+    return k;
 }
 
 extern "C" int mfk_kmf_sse_plan(const mfk_plan *plan, int kernel, const float *d_P, const float *d_Q,
@@ -203,16 +222,14 @@ extern "C" int mfk_kmf_sse_plan(const mfk_plan *plan, int kernel, const float *d
                                 float global_mean, float gamma, float min_rating, float max_rating, void *d_ws,
                                 double *d_sse, void *stream) {
     MFK_REQUIRE(plan != nullptr, "mfk_kmf_sse_plan: plan is NULL");
-    if (!plan->hot)
-        return mfk_kmf_sse(kernel, plan->su, plan->si, plan->sr, plan->n, d_P, d_Q, d_bu, d_bi, n_factors, ld,
-                           global_mean, gamma, min_rating, max_rating, d_ws, d_sse, stream);
     MFK_REQUIRE(kernel >= 0 && kernel <= 2, "mfk_kmf_sse_plan: bad kernel %d", kernel);
     int rc = check_factors("mfk_kmf_sse_plan", d_P, d_Q, d_bu, d_bi, n_factors, ld);
     if (rc) return rc;
     EvalParams e{d_P, d_Q, d_bu, d_bi, (n_factors + 3) & ~3, ld, global_mean, gamma, min_rating,
                  max_rating - min_rating};
-    return run_sse(kernel, false, plan->su, plan->si, plan->sr, plan->n, e, d_ws, d_sse, as_stream(stream),
-                   plan->hot->su, plan->hot->si, plan->hot->sr, plan->hot->n);
+    RatingSeg segs[kMaxSegs];
+    const int n_segs = plan_segments(plan, segs);
+    return run_sse(kernel, false, segs, n_segs, e, d_ws, d_sse, as_stream(stream));
 }
 
 extern "C" int mfk_kmf_predict(int kernel, const int32_t *d_u, const int32_t *d_i, int64_t n, const float *d_P,
@@ -242,7 +259,8 @@ extern "C" int mfk_bias_sse(const int32_t *d_u, const int32_t *d_i, const float 
                             const float *d_bi, float global_mean, void *d_ws, double *d_sse, void *stream) {
     MFK_REQUIRE(d_bu && d_bi, "mfk_bias_sse: null bias array");
     EvalParams e{nullptr, nullptr, d_bu, d_bi, 0, 0, global_mean, 0.f, 0.f, 0.f};
-    return run_sse(0, true, d_u, d_i, d_r, n, e, d_ws, d_sse, as_stream(stream));
+    const RatingSeg seg{d_u, d_i, d_r, n};
+    return run_sse(0, true, &seg, 1, e, d_ws, d_sse, as_stream(stream));
 }
 
 extern "C" int mfk_bias_predict(const int32_t *d_u, const int32_t *d_i, int64_t n, const float *d_bu,

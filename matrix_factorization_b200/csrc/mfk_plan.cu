@@ -15,6 +15,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdarg>
+#include <cstring>
 #include <vector>
 
 #include "mfk_common.cuh"
@@ -103,14 +104,14 @@ __global__ void k_deal(const int32_t *__restrict__ sorted_ids, int32_t n_ids, in
 
 __global__ void k_keys(const int32_t *__restrict__ u, const int32_t *__restrict__ i, int64_t n,
                        const int32_t *__restrict__ ustripe, const int32_t *__restrict__ iworker,
-                       const int32_t *__restrict__ islot, int32_t W, uint64_t *keys, int32_t *idx) {
+                       const int32_t *__restrict__ islot, int32_t R, int32_t slack, uint64_t *keys, int32_t *idx) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; k < n; k += stride) {
         int32_t ii = i[k];
         int32_t w = iworker[ii];
-        int32_t s = ustripe[u[k]] - w;
-        if (s < 0) s += W;
+        int32_t s = ustripe[u[k]] - slack * w;  // worker w meets stripe (slack * w + s) mod R at step s
+        if (s < 0) s += R;
         keys[k] = ((uint64_t)w << kPlanWorkerShift) | ((uint64_t)s << kPlanStepShift) | (uint64_t)islot[ii];
         idx[k] = (int32_t)k;
     }
@@ -140,21 +141,29 @@ __global__ void k_gather(const uint64_t *__restrict__ keys, const int32_t *__res
 //   kCtrlQuad    records k..k+3 have the same (worker, step, slot) key and none of them is a dup, so
 //                the four users are distinct and the kernel may resolve them as one exact 4-chain;
 //   kCtrlNewStep / kCtrlNewItem   block and item boundaries inside a worker's list.
+//   kCtrlOwn     the user occurs among the previous 15 records OF THIS WORKER: the user's previous rating in
+//                the emitted order is then that record (a user meets a worker in one step only).
+// need (nullable): per record, the number of earlier ratings of its user (dataflow schedule); it replaces
+// the step in the low bits of ctrl.
 __global__ void k_build_records(const uint64_t *__restrict__ keys, const int32_t *__restrict__ su,
-                                const float *__restrict__ sr, int64_t n, int32_t n_users, int4 *rec) {
+                                const float *__restrict__ sr, const int32_t *__restrict__ need, int64_t n,
+                                int32_t n_users, int4 *rec) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     const uint64_t slot_mask = (1ull << kPlanStepShift) - 1;
     for (; k < n; k += stride) {
         const uint64_t key = keys[k];
-        auto is_dup = [&](int64_t x) {
-            int32_t u = su[x];
-            // users of the last partial 16-byte bias chunk are read directly too (no over-read of bu)
-            bool d = (u | 3) >= n_users;
-            for (int j = 1; j <= 15 && x - j >= 0; ++j) d |= (su[x - j] == u);
+        auto is_own = [&](int64_t x) {
+            const int32_t u = su[x];
+            const uint64_t wk = keys[x] >> kPlanWorkerShift;
+            bool d = false;
+            for (int j = 1; j <= 15 && x - j >= 0; ++j) d |= (su[x - j] == u && (keys[x - j] >> kPlanWorkerShift) == wk);
             return d;
         };
-        int32_t ctrl = (int32_t)((key >> kPlanStepShift) & 0xffff);
+        // users of the last partial 16-byte bias chunk are read directly too (no over-read of bu)
+        auto is_dup = [&](int64_t x) { return (su[x] | 3) >= n_users || is_own(x); };
+        int32_t ctrl = need ? (need[k] & kNeedMask) : (int32_t)((key >> kPlanStepShift) & 0xffff);
+        if (is_own(k)) ctrl |= kCtrlOwn;
         const bool dup = is_dup(k);
         if (dup) ctrl |= kCtrlDup;
         if (k == 0 || (keys[k - 1] >> kPlanStepShift) != (key >> kPlanStepShift)) ctrl |= kCtrlNewStep;
@@ -179,6 +188,24 @@ __global__ void k_worker_bounds(const uint64_t *__restrict__ keys, int64_t n, in
         else hi = mid;
     }
     wbeg[w] = lo;
+}
+
+// dataflow schedule: key (user, step) of every list position
+__global__ void k_user_step_keys(const int32_t *__restrict__ su, const int32_t *__restrict__ sstep, int64_t n,
+                                 uint64_t *keys, int32_t *pos) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < n; k += stride) {
+        keys[k] = ((uint64_t)(uint32_t)su[k] << 16) | (uint64_t)(uint32_t)sstep[k];
+        pos[k] = (int32_t)k;
+    }
+}
+// j-th entry of the (user, step)-sorted list is the (j - ustart[user])-th rating of its user
+__global__ void k_user_ranks(const uint64_t *__restrict__ keys_sorted, const int32_t *__restrict__ pos_sorted,
+                             const int32_t *__restrict__ ustart, int64_t n, int32_t *need) {
+    int64_t j = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; j < n; j += stride) need[pos_sorted[j]] = (int32_t)(j - (int64_t)ustart[keys_sorted[j] >> 16]);
 }
 
 __global__ void k_pos_iota(int32_t *a, int64_t n) {

@@ -7,17 +7,23 @@ namespace mfk {
 // sort key: [worker | step | slot]
 constexpr int kPlanWorkerShift = 40;
 constexpr int kPlanStepShift = 24;
-// ctrl word of a schedule record: step in the low 16 bits, then flags
+// ctrl word of a schedule record: flags in the high bits; the low bits hold the step (ring schedule, 16 bits) or
+// the number of earlier ratings of the same user in the emitted order (dataflow schedule, 26 bits)
 constexpr int32_t kCtrlDup = 1 << 30;      // this user occurs among the previous 15 records (do not prefetch its row)
 constexpr int32_t kCtrlQuad = 1 << 29;     // records k..k+3 share worker, step and item, none is kCtrlDup
 constexpr int32_t kCtrlNewStep = 1 << 28;  // first record of a (worker, step) block
 constexpr int32_t kCtrlNewItem = 1 << 27;  // item differs from the previous record of this worker
+constexpr int32_t kCtrlOwn = 1 << 26;      // the user's previous rating is one of this worker's previous 15 records
+constexpr int32_t kNeedMask = (1 << 26) - 1;
+constexpr int32_t kDefaultSlack = 1;       // stripes per worker when mfk_plan_opts.stripe_slack is 0
 }  // namespace mfk
 
 struct mfk_plan {
     int64_t n = 0;
     int32_t n_users = 0, n_items = 0;
-    int32_t W = 0;  // worker warps == user stripes == steps
+    int32_t W = 0;  // worker warps
+    int32_t slack = 1;  // stripes per worker: step s of worker w needs step s - slack of worker w + 1
+    int32_t R = 0;      // user stripes == steps per epoch == slack * W
     int32_t n_ctas = 0, warps_per_cta = 0;
     int32_t max_slots = 0;  // items per worker (rows of witems)
     int64_t max_worker_ratings = 0, max_item_degree = 0, max_user_degree = 0;
@@ -34,11 +40,17 @@ struct mfk_plan {
     int32_t *iworker = nullptr, *islot = nullptr;  // per item
     int32_t *ustripe = nullptr;                    // per user
     int32_t *flags = nullptr;  // [W] ring progress flags (monotone across epochs)
+    int32_t flow = 0;          // 1: dataflow schedule (records carry the user's version, uver is the live counter)
+    int32_t *uver = nullptr;   // [n_users] ratings of each user applied so far in this epoch (dataflow schedule)
     // hot/cold split (optional): `hot` is a plan over the ratings of the most-rated items (one item per
     // worker, worker = one CTA); this plan then covers the remaining ratings.  n_total counts both.
     mfk_plan *hot = nullptr;
+    // `hot_users`: likewise for the most active users among the remaining ratings, built with the roles of users
+    // and items exchanged (swapped = 1: su holds item ids, si user ids, the workers own users)
+    mfk_plan *hot_users = nullptr;
+    int32_t n_hot_users = 0, swapped = 0;
     int64_t n_total = 0;
     int32_t n_hot_items = 0;
     long long *stats = nullptr;  // [W][4] per-worker counters of the last SGD epoch (diagnostics)
-    int64_t epoch = 0;         // epochs run so far (flag base = epoch * (W + 1))
+    int64_t epoch = 0;         // epochs run so far (flag base = epoch * (R + 1))
 };

@@ -50,8 +50,11 @@ struct RingView {
     const int32_t *witems;
     int32_t *flags;
     int32_t W, k, max_slots;
+    int32_t R, slack;  // steps per epoch (= stripes = slack * W); step s needs the neighbour's step s - slack
     int32_t depth;  // prefetch ring depth D (2..kRingDepthMax)
     unsigned long long watchdog_ns;  // trap if a wait sees no progress for this long (0 = never)
+    uint32_t max_sleep_ns;           // cap of the poll back-off
+    int32_t *uver;                   // [n_users] per-user version counters (dataflow schedule), zero at epoch start
     long long *stats;                // [W][4]: total cycles, cycles blocked in hand-off waits, 4-chains, singles
     long long *prof;                 // [W][8]: phase cycle counters (only written by MFK_RING_PROFILE builds)
 };
@@ -72,6 +75,8 @@ struct Ring {
     int32_t *gpub;             // global flag this warp publishes (warp 0 only) or nullptr
     const int32_t *gpoll;      // global flag this warp polls (last warp only) or nullptr
     int32_t warp, base, pub, rel, pending;
+    uint32_t max_ns;  // cap of the poll back-off
+    int32_t ahead;  // slack - 1: how many steps beyond the neighbour's completed count may be entered
     int32_t last_rel;
     unsigned long long t0, watchdog_ns;
     long long wait_cycles;
@@ -106,14 +111,14 @@ struct Ring {
             int32_t f = load_flag();
             if (f > rel) {
                 rel = f;
-                int32_t t = min(cap, rel + 1);
+                int32_t t = min(cap, rel + 1 + ahead);
                 if (t > pub) publish(t);
                 if (rel >= target) break;
                 ns = 64;
                 continue;
             }
             __nanosleep(ns);
-            if (ns < 2048) ns <<= 1;
+            if (ns < max_ns) ns <<= 1;
             if (((++it) & 0x3ffu) == 0 && watchdog_ns) {  // a ring without progress for seconds is a bug: trap
                 unsigned long long now;
                 asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
@@ -123,27 +128,29 @@ struct Ring {
         }
         wait_cycles += clock64() - c0;
     }
-    // Block until every step < s of the neighbour is complete.
+    // may step s be entered (its stripe was released by the neighbour's step s - slack)?
+    __device__ __forceinline__ bool open(int32_t s) const { return s <= rel + ahead; }
+    // Block until the neighbour has completed every step <= s - slack.
     __device__ __forceinline__ void advance_to(int32_t s) {
         if (dirty) {
             if (!gpub) asm volatile("fence.acq_rel.cta;" ::: "memory");  // CTA-scope release; gpu scope rides on st.release
             dirty = false;
         }
-        int32_t t = min(s, rel + 1);
+        int32_t t = min(s, rel + 1 + ahead);
         if (t > pub) publish(t);
-        if (rel >= s) return;
-        wait_for(s, s);
+        if (open(s)) return;
+        wait_for(s - ahead, s);
     }
-    // After the last rating: keep forwarding until the whole ring has drained (pub == W).
+    // After the last rating: keep forwarding until the whole ring has drained (pub == R, the step count).
     __device__ __forceinline__ void finish(int32_t W) {
         if (dirty) {
             if (!gpub) asm volatile("fence.acq_rel.cta;" ::: "memory");
             dirty = false;
         }
-        int32_t t = min(W, rel + 1);
+        int32_t t = min(W, rel + 1 + ahead);
         if (t > pub) publish(t);
         if (pub >= W) return;
-        wait_for(W - 1, W);  // rel >= W-1  =>  pub == W
+        wait_for(W - 1 - ahead, W);  // rel >= W-1-ahead  =>  pub == W
     }
 };
 
@@ -334,7 +341,15 @@ constexpr int ring_max_threads() {
     return NV >= 8 ? 256 : 512;  // >= 128 registers per thread: the chain code must not spill or rematerialise
 }
 
-template <int KERNEL, int NV, bool QSMEM>
+constexpr int kFlowBatch = 4;        // finished ratings published per memory fence (dataflow schedule)
+constexpr uint32_t kFlowAhead = 24;  // look for more ready records when fewer than this many are known ahead
+
+// FLOW = false: ring schedule -- workers hand whole user stripes around (Ring above).
+// FLOW = true:  dataflow schedule -- a record carries the number of earlier ratings of its user (`need`); it may be
+//   applied once uver[user] == need, and applying it publishes need + 1.  Workers walk their lists in order, so
+//   the emitted order (a linear extension of the per-worker and per-user orders) is reproduced exactly while
+//   every rating only waits for the one rating it really depends on.
+template <int KERNEL, int NV, bool QSMEM, bool FLOW>
 __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView rv, SgdParams prm) {
     extern __shared__ __align__(16) unsigned char smem_raw[];
     int32_t *sflags = reinterpret_cast<int32_t *>(smem_raw);  // [32]
@@ -391,6 +406,8 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
     ring.t0 = 0;
     ring.watchdog_ns = rv.watchdog_ns;
     ring.wait_cycles = 0;
+    ring.ahead = rv.slack - 1;
+    ring.max_ns = rv.max_sleep_ns;
     const long long clk_start = clock64();
     int32_t n_quads = 0, n_singles = 0;
 #if MFK_RING_PROFILE
@@ -468,21 +485,96 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
     const float ap = prm.upd_user ? 1.0f - prm.lr * prm.reg : 1.0f, lp = prm.upd_user ? prm.lr : 0.f;
     const float aq2 = aq * aq, aq3 = aq2 * aq;
 
+    // ---- dataflow state: records [0, rdy_end) are known ready; one poll of the next <= 32 records may be in flight
+    uint32_t rdy_end = (FLOW && prm.upd_user) ? 0u : n_list;  // users that are only read never block anybody
+    bool f_polling = false;
+    int32_t f_ver = 0, f_need = 0;  // lane j: version seen / needed by record rdy_end + j
+    int32_t pend_u = 0, pend_v = 0, n_pend = 0;  // lane j < n_pend: version pend_v of user pend_u awaits publication
+    auto flow_poll = [&](uint32_t w0_) {
+        const uint32_t x = rdy_end + (uint32_t)lane;
+        f_need = INT32_MAX;
+        f_ver = 0;
+        if (x < n_list && x < w0_ + 64u) {
+            const int4 rp = srec[x & 63u];
+            f_need = rp.w & kNeedMask;
+            f_ver = (rp.w & kCtrlOwn) ? INT32_MAX : ld_strong_i(rv.uver + rp.x);
+        }
+        f_polling = true;
+    };
+    auto flow_consume = [&]() {
+        const unsigned m = __ballot_sync(0xffffffffu, f_ver >= f_need);
+        rdy_end += (m == 0xffffffffu) ? 32u : (uint32_t)(__ffs((int)~m) - 1);
+        f_polling = false;
+    };
+    // publish the versions of the ratings applied since the last flush: every lane fences its own row stores first
+    auto flow_flush = [&]() {
+        if (n_pend == 0) return;
+        asm volatile("fence.release.gpu;" ::: "memory");  // MEMBAR.ALL.GPU, no L1 invalidation
+        __syncwarp();
+        // max, not store: one flush may carry several versions of the same user (its ratings in this cell)
+        if (lane < n_pend) asm volatile("red.relaxed.gpu.global.max.s32 [%0], %1;" ::"l"(rv.uver + pend_u), "r"(pend_v) : "memory");
+        n_pend = 0;
+    };
+    auto flow_done = [&](int32_t user, int32_t ctl) {
+        if (lane == n_pend) {
+            pend_u = user;
+            pend_v = (ctl & kNeedMask) + 1;
+        }
+        ++n_pend;
+    };
+
     uint32_t k = 0;
     bool first = true;
     while (k < n_list) {
         PROF_T0();
         const int4 rc = srec[k & 63u];
         const int32_t ctrl = rc.w;
-        if (first || (ctrl & kCtrlNewStep)) ring.advance_to(ctrl & 0xffff);
+        if constexpr (FLOW) {
+            if (f_polling) flow_consume();
+            // a 4-chain is entered only with all four ratings ready: whether ratings are resolved as a chain or one
+            // by one must not depend on timing (the two differ in rounding)
+            const uint32_t head_end = k + ((kQuads && (ctrl & kCtrlQuad) && D >= 4) ? 4u : 1u);
+            if (rdy_end < head_end) {
+                // the head record waits for another worker: publish what we owe, then poll with back-off
+                flow_flush();
+                const long long c0 = clock64();
+                unsigned ns = 32, it = 0;
+                for (;;) {
+                    flow_poll(w0);
+                    flow_consume();
+                    if (rdy_end >= head_end) break;
+                    __nanosleep(ns);
+                    if (ns < rv.max_sleep_ns) ns <<= 1;
+                    if (((++it) & 0x3ffu) == 0 && ring.watchdog_ns) {
+                        unsigned long long now;
+                        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(now));
+                        if (ring.t0 == 0) ring.t0 = now;
+                        else if (now - ring.t0 > ring.watchdog_ns) {
+                            if (lane == 0) {
+                                const int4 rb = srec[k & 63u];
+                                printf("mfk flow watchdog: worker %d record %u of %u (user %d, needs version %d, sees %d)\n", w, k,
+                                       n_list, rb.x, rb.w & kNeedMask, ld_strong_i(rv.uver + rb.x));
+                            }
+                            __trap();
+                        }
+                    }
+                }
+                ring.t0 = 0;
+                ring.wait_cycles += clock64() - c0;
+            }
+            if (rdy_end < n_list && rdy_end < k + kFlowAhead && rdy_end < w0 + 64u) flow_poll(w0);
+        }
+        if constexpr (!FLOW) {
+            if (first || (ctrl & kCtrlNewStep)) ring.advance_to(ctrl & 0xffff);
+        }
         PROF_ADD(0);
         // issue as far as the ring depth, the record window and the neighbour's progress allow
         {
-            const uint32_t lim = min(min(n_list, k + (uint32_t)D), w0 + 64u);
+            const uint32_t lim = min(min(min(n_list, k + (uint32_t)D), w0 + 64u), rdy_end);
             if (pf + 4u <= lim) {  // common case in a chain: four at once, one progress check
                 const int4 a0 = srec[pf & 63u], a1 = srec[(pf + 1u) & 63u], a2 = srec[(pf + 2u) & 63u],
                            a3 = srec[(pf + 3u) & 63u];
-                if ((a3.w & 0xffff) <= ring.rel) {
+                if (FLOW || ring.open(a3.w & 0xffff)) {
                     if (has_bias && lane < 4) {  // the four bias chunks with one instruction (lane j -> index pf+j)
                         const int32_t uj = lane == 0 ? a0.x : (lane == 1 ? a1.x : (lane == 2 ? a2.x : a3.x));
                         const int32_t cj = lane == 0 ? a0.w : (lane == 1 ? a1.w : (lane == 2 ? a2.w : a3.w));
@@ -497,9 +589,9 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
             }
             while (pf < lim) {
                 const int4 rp = srec[pf & 63u];
-                if ((rp.w & 0xffff) > ring.rel) {
+                if (!FLOW && !ring.open(rp.w & 0xffff)) {
                     ring.refresh_async();  // non-blocking look at the neighbour; otherwise retry next rating
-                    if ((rp.w & 0xffff) > ring.rel) break;
+                    if (!ring.open(rp.w & 0xffff)) break;
                 }
                 issue(pf, rp.x, rp.w);
                 ++pf;
@@ -585,6 +677,13 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
                 prm.bu[r2.x] = fmaf(-lp, e2, ap * ub2);
                 prm.bu[r3.x] = fmaf(-lp, e3, ap * ub3);
                 ring.dirty = true;
+                if constexpr (FLOW) {
+                    flow_done(u, ctrl);
+                    flow_done(r1.x, r1.w);
+                    flow_done(r2.x, r2.w);
+                    flow_done(r3.x, r3.w);
+                    flow_flush();
+                }
             }
             ib = fmaf(-lq, e0, aq * ib);
             ib = fmaf(-lq, e1, aq * ib);
@@ -623,6 +722,10 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
                 if (NV > 0) store_row<NVR>(p, prm.P + (size_t)u * ld, lane, F);
                 if (has_bias) prm.bu[u] = ub;  // every lane stores the same value (own program order)
                 ring.dirty = true;
+                if constexpr (FLOW) {
+                    flow_done(u, ctrl);
+                    if (n_pend >= kFlowBatch) flow_flush();
+                }
             }
             k += 1u;
             ++n_singles;
@@ -639,7 +742,8 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
     }
     flush_q();
     const long long clk_work = clock64();
-    ring.finish(rv.W);
+    if constexpr (FLOW) flow_flush();
+    else ring.finish(rv.R);
     if (rv.stats && lane == 0) {
         rv.stats[4 * (int64_t)w + 0] = clk_work - clk_start;
         rv.stats[4 * (int64_t)w + 1] = ring.wait_cycles;
@@ -675,6 +779,9 @@ static int launch_ring(const mfk_plan *plan, const SgdParams &prm, int depth, si
     rv.witems = plan->witems;
     rv.flags = plan->flags;
     rv.W = plan->W;
+    rv.R = plan->R;
+    rv.slack = plan->slack;
+    rv.uver = plan->uver;
     rv.k = plan->warps_per_cta;
     rv.max_slots = plan->max_slots;
     rv.depth = depth;
@@ -686,8 +793,11 @@ static int launch_ring(const mfk_plan *plan, const SgdParams &prm, int depth, si
             return e ? atoll(e) : 10000ll;
         }();
         rv.watchdog_ns = wd_ms > 0 ? (unsigned long long)wd_ms * 1000000ull : 0ull;
+        const char *e = getenv("MFK_RING_SLEEP_NS");
+        rv.max_sleep_ns = e ? (uint32_t)atoi(e) : 2048u;
     }
-    auto kern = k_sgd_ring<KERNEL, NV, QSMEM>;
+    auto kern = plan->flow ? k_sgd_ring<KERNEL, NV, QSMEM, true> : k_sgd_ring<KERNEL, NV, QSMEM, false>;
+    if (plan->flow) MFK_CUDA(cudaMemsetAsync(plan->uver, 0, sizeof(int32_t) * (size_t)plan->n_users, st));
     if (plan->warps_per_cta * 32 > ring_max_threads<NV>()) {
         set_error("sgd ring: plan has %d warps per CTA but rows of %d floats allow at most %d; rebuild the plan with "
                   "mfk_plan_opts.n_factors set", plan->warps_per_cta, prm.F, ring_max_threads<NV>() / 32);
@@ -742,9 +852,22 @@ static int launch_ring_nv(const mfk_plan *plan, const SgdParams &prm, cudaStream
     return launch_ring_q<KERNEL, 8>(plan, prm, st);
 }
 
+// parameters for a role-swapped sub-plan (its "users" are items and vice versa)
+static SgdParams swap_roles(const SgdParams &prm, const mfk_plan *sub) {
+    SgdParams s = prm;
+    s.P = prm.Q;
+    s.Q = prm.P;
+    s.bu = prm.bi;
+    s.bi = prm.bu;
+    s.upd_user = prm.upd_item;
+    s.upd_item = prm.upd_user;
+    s.n_users = sub->n_users;
+    return s;
+}
+
 static int32_t next_base(mfk_plan *plan, cudaStream_t st, int *rc) {
     *rc = MFK_OK;
-    int64_t base = plan->epoch * (int64_t)(plan->W + 1);
+    int64_t base = plan->epoch * (int64_t)(plan->R + 1);
     if (base > (int64_t)1 << 30) {  // keep the monotone flags inside int32
         cudaError_t e = cudaMemsetAsync(plan->flags, 0, sizeof(int32_t) * (size_t)(plan->W + 32), st);
         if (e != cudaSuccess) {
@@ -810,6 +933,20 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         else rc = launch_ring_nv<MFK_KERNEL_RBF>(hot, hp, st);
         if (rc) return rc;
     }
+    if (plan->hot_users && plan->hot_users->n > 0) {
+        // then the most active users: the update rules are symmetric in (p_u, b_u) <-> (q_i, b_i), so the same
+        // kernels run on the role-swapped sub-plan with the parameter arrays exchanged
+        mfk_plan *hu = plan->hot_users;
+        SgdParams hp = swap_roles(prm, hu);
+        hp.base = next_base(hu, st, &rc);
+        if (rc) return rc;
+        if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128) rc = launch_hot<1>(hu, hp, st);
+        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256) rc = launch_hot<2>(hu, hp, st);
+        else if (kernel == MFK_KERNEL_LINEAR) rc = launch_ring_nv<MFK_KERNEL_LINEAR>(hu, hp, st);
+        else if (kernel == MFK_KERNEL_SIGMOID) rc = launch_ring_nv<MFK_KERNEL_SIGMOID>(hu, hp, st);
+        else rc = launch_ring_nv<MFK_KERNEL_RBF>(hu, hp, st);
+        if (rc) return rc;
+    }
     if (plan->n == 0) return MFK_OK;
     prm.base = next_base(plan, st, &rc);
     if (rc) return rc;
@@ -847,6 +984,13 @@ extern "C" int mfk_bias_sgd_epoch(mfk_plan *plan, float *d_bu, float *d_bi, floa
         hp.base = next_base(plan->hot, st, &rc);
         if (rc) return rc;
         rc = launch_ring_q<MFK_KERNEL_LINEAR, 0>(plan->hot, hp, st);
+        if (rc) return rc;
+    }
+    if (plan->hot_users && plan->hot_users->n > 0) {
+        SgdParams hp = swap_roles(prm, plan->hot_users);
+        hp.base = next_base(plan->hot_users, st, &rc);
+        if (rc) return rc;
+        rc = launch_ring_q<MFK_KERNEL_LINEAR, 0>(plan->hot_users, hp, st);
         if (rc) return rc;
     }
     if (plan->n == 0) return MFK_OK;

@@ -67,12 +67,14 @@ class Plan:
     NO_HOT_SPLIT = 0xFFFFFFFF
 
     def __init__(self, u, i, r, n_users: int, n_items: int, n_factors: int = 0, n_workers: int = 0,
-                 warps_per_cta: int = 0, hot_min_degree: int = NO_HOT_SPLIT):
+                 warps_per_cta: int = 0, hot_min_degree: int = NO_HOT_SPLIT, stripe_slack: int = 0,
+                 schedule: int = 0, hot_users: bool = True):
         torch = _torch()
         assert u.dtype == torch.int32 and i.dtype == torch.int32 and r.dtype == torch.float32
         self._h = C.c_void_p()
         self.n = int(u.numel())
-        opts = PlanOpts(int(n_workers), int(warps_per_cta), int(n_factors), int(hot_min_degree))
+        opts = PlanOpts(int(n_workers), int(warps_per_cta), int(n_factors), int(hot_min_degree), int(stripe_slack), int(schedule),
+                        0 if hot_users else 1)
         check(lib().mfk_plan_create(C.byref(self._h), ptr(u), ptr(i), ptr(r), self.n, int(n_users), int(n_items),
                                     C.byref(opts), stream_ptr()))
 
@@ -103,14 +105,17 @@ class Plan:
         """[n_workers, 4] int64 host array: cycles, blocked cycles, 4-chains, singles of the last epoch."""
         torch = _torch()
         info = self.info()
-        W, H = info["n_workers"], info["n_hot_items"]
-        out = torch.zeros((12 * (W + H),), dtype=torch.int64, device=device())
+        W, H, HU = info["n_workers"], info["n_hot_items"], info["n_hot_users"]
+        out = torch.zeros((12 * (W + H + HU),), dtype=torch.int64, device=device())
         check(lib().mfk_plan_stats(self._h, ptr(out), stream_ptr()))
         out = out.cpu().numpy()
         self.last_profile = out[4 * W:12 * W].reshape(W, 8)  # phase counters (MFK_RING_PROFILE builds only)
-        hot = out[12 * W:]
+        hot = out[12 * W:12 * (W + H)]
         self.hot_stats = hot[:4 * H].reshape(H, 4)    # cycles, blocked cycles, batches, ratings per hot item
         self.hot_profile = hot[4 * H:].reshape(H, 8)  # phase cycles of the hot kernel
+        hotu = out[12 * (W + H):]
+        self.hot_user_stats = hotu[:4 * HU].reshape(HU, 4)
+        self.hot_user_profile = hotu[4 * HU:].reshape(HU, 8)
         return out[:4 * W].reshape(W, 4)
 
     def close(self):

@@ -46,16 +46,25 @@ def test_plan_is_conflict_free_and_order_is_permutation():
     u, i, r, *_ = _problem(1, 300, 200, 9000, 4, hot=0.05)
     du, di, dr = (torch.tensor(u, dtype=torch.int32).cuda(), torch.tensor(i, dtype=torch.int32).cuda(),
                   torch.tensor(r, dtype=torch.float32).cuda())
-    for opts in [dict(), dict(n_workers=16, warps_per_cta=4), dict(n_workers=7, warps_per_cta=7), dict(n_workers=1, warps_per_cta=1)]:
+    for opts in [dict(), dict(n_workers=16, warps_per_cta=4), dict(n_workers=7, warps_per_cta=7), dict(n_workers=1, warps_per_cta=1),
+                 dict(stripe_slack=1), dict(stripe_slack=3), dict(n_workers=16, warps_per_cta=4, stripe_slack=4),
+                 dict(schedule=2), dict(schedule=1)]:
         plan = engine.Plan(du, di, dr, 300, 200, n_factors=4, **opts)
         info = plan.info()
-        W = info["n_workers"]
+        W, R = info["n_workers"], info["n_steps"]
         assert W == info["n_ctas"] * info["warps_per_cta"]
+        assert R % W == 0 and (opts.get("stripe_slack", 0) in (0, R // W))
         w, s = (t.cpu().numpy().astype(np.int64) for t in plan.assignment())
         order = plan.order().cpu().numpy()
         assert np.array_equal(np.sort(order), np.arange(len(u)))          # permutation
         assert np.all(np.diff(s[order]) >= 0)                              # step-major
-        assert s.min() >= 0 and s.max() < W and w.max() < W
+        assert s.min() >= 0 and s.max() < R and w.max() < W
+        # a user's stripe (c * worker + step) mod R is the same wherever the user is rated: the stripe travels
+        # around the ring, worker w + 1 hands it to worker w with a lag of c = R / W steps
+        stripe = ((R // W) * w + s) % R
+        first = np.full(300, -1, np.int64)
+        first[u[::-1]] = stripe[::-1]
+        assert np.array_equal(stripe, first[u])
         # inside one step (wave) a user / an item is touched by exactly one worker
         for ids in (u, i):
             key = s * (ids.max() + 1) + ids
@@ -73,7 +82,9 @@ def test_one_epoch_matches_reference_replay(golden_dir, kname, flags):
     kmf, orc = _mods()
     g = np.load(os.path.join(golden_dir, f"replay_{kname}_{flags}.npz"))
     uu, ui = flags[0] == "1", flags[1] == "1"
-    for opts in [None, dict(n_workers=6, warps_per_cta=3), dict(n_workers=24, warps_per_cta=4)]:
+    for opts in [None, dict(n_workers=6, warps_per_cta=3), dict(n_workers=24, warps_per_cta=4),
+                 dict(n_workers=6, warps_per_cta=3, stripe_slack=2), dict(stripe_slack=4),
+                 dict(schedule=2), dict(n_workers=6, warps_per_cta=3, stripe_slack=2, schedule=2)]:
         P, Q, bu, bi = (g[k].copy() for k in ("P0", "Q0", "bu0", "bi0"))
         X = np.stack([g["u"], g["i"], g["r"]], axis=1).astype(np.float64)
         P2, Q2, bu2, bi2, rm, order = kmf._sgd(X, float(g["mu"]), bu, bi, P, Q, 1, kname, float(g["gamma"]),

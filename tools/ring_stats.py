@@ -37,7 +37,8 @@ def main():
     info = plan.info()
     w, s = plan.assignment()
     H = info["n_hot_items"]
-    w, s = w[w >= H] - H, s[w >= H] - H  # cold workers only (hot workers / steps are numbered first)
+    HH = H + info["n_hot_users"]
+    w, s = w[w >= HH] - HH, s[w >= HH] - HH  # cold workers only (the workers / steps of the hot phases are numbered first)
     counts = torch.bincount(w.long(), minlength=info["n_workers"]).cpu().numpy()
     steps_nonempty = torch.unique(w.long() * 65536 + s.long()).div(65536, rounding_mode="floor").bincount(minlength=info["n_workers"]).cpu().numpy()
     ms = []
@@ -67,6 +68,12 @@ def main():
     print("median worker:", med, counts[med], steps_nonempty[med], st[med, 0] / 1e6, st[med, 1] / 1e6, busy[med] / max(1, counts[med]), st[med, 2], st[med, 3])
     print("busy cycles/rating percentiles (all workers):", np.percentile(busy / np.maximum(1, counts), [5, 50, 95]))
     print("sum busy Mcyc", busy.sum() / 1e6, "max total Mcyc", st[:, 0].max() / 1e6)
+    for label, hs, hp in (("hot item", plan.hot_stats, plan.hot_profile), ("hot user", plan.hot_user_stats, plan.hot_user_profile)):
+        if not len(hs):
+            continue
+        x = int(np.argmax(hs[:, 0]))
+        print(label, "phase:", len(hs), "workers, max Mcyc", hs[:, 0].max() / 1e6, "ratings max", hs[:, 3].max(), "sum", hs[:, 3].sum(),
+              "slowest: blocked Mcyc", hs[x, 1] / 1e6, "batches", hs[x, 2], "ratings", hs[x, 3])
     if H:
         hs, hp = plan.hot_stats, plan.hot_profile
         top = np.argsort(-hs[:, 3])[:3]
