@@ -70,7 +70,7 @@ typedef struct {
     uint32_t stripe_slack; /* user stripes per worker (steps per epoch = stripe_slack * n_workers): step s of a
                               worker needs step s - stripe_slack of its ring neighbour, so a worker may run
                               stripe_slack - 1 steps ahead of the hand-off; 0 = default */
-    uint32_t schedule;     /* how the workers synchronise: 0 = default (1), 1 = dataflow -- every rating waits for
+    uint32_t schedule;     /* how the workers synchronise: 0 = default (2), 1 = dataflow -- every rating waits for
                               exactly the previous rating of its user (per-user version counters), 2 = ring --
                               workers hand whole user stripes around in lockstep */
     uint32_t no_hot_users; /* 1 = split off hot items only (by default the most active users among the remaining

@@ -104,7 +104,8 @@ __global__ void k_deal(const int32_t *__restrict__ sorted_ids, int32_t n_ids, in
 
 __global__ void k_keys(const int32_t *__restrict__ u, const int32_t *__restrict__ i, int64_t n,
                        const int32_t *__restrict__ ustripe, const int32_t *__restrict__ iworker,
-                       const int32_t *__restrict__ islot, int32_t R, int32_t slack, uint64_t *keys, int32_t *idx) {
+                       const int32_t *__restrict__ islot, const uint8_t *__restrict__ layer /* nullable */, int32_t R,
+                       int32_t slack, uint64_t *keys, int32_t *idx) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; k < n; k += stride) {
@@ -112,7 +113,8 @@ __global__ void k_keys(const int32_t *__restrict__ u, const int32_t *__restrict_
         int32_t w = iworker[ii];
         int32_t s = ustripe[u[k]] - slack * w;  // worker w meets stripe (slack * w + s) mod R at step s
         if (s < 0) s += R;
-        keys[k] = ((uint64_t)w << kPlanWorkerShift) | ((uint64_t)s << kPlanStepShift) | (uint64_t)islot[ii];
+        keys[k] = ((uint64_t)w << kPlanWorkerShift) | ((uint64_t)s << kPlanStepShift) |
+                  ((uint64_t)(layer ? layer[k] : 0) << kPlanLayerShift) | (uint64_t)islot[ii];
         idx[k] = (int32_t)k;
     }
 }
@@ -129,20 +131,40 @@ __global__ void k_gather(const uint64_t *__restrict__ keys, const int32_t *__res
         su[k] = u[j];
         si[k] = i[j];
         sr[k] = r[j];
-        sslot[k] = (int32_t)(key & ((1ull << kPlanStepShift) - 1));
+        sslot[k] = (int32_t)(key & ((1ull << kPlanLayerShift) - 1));
         sstep[k] = (int32_t)((key >> kPlanStepShift) & ((1ull << (kPlanWorkerShift - kPlanStepShift)) - 1));
     }
 }
 
-// Schedule records streamed by the SGD kernel: {user, slot, rating bits, ctrl} with
-//   kCtrlDup     user occurs among the previous 15 records (the kernel prefetches user rows up to 8
-//                ratings ahead and must not prefetch a row it is about to rewrite), or belongs to the
+// Order inside a (worker, step) block.  After a first sort by (worker, step, slot), the c ratings of one item in
+// one block split into a chain part -- the first 4 * (c / 4), which stay together and are resolved as exact
+// 4-chains -- and a remainder of up to three, which goes to layers 1..3: layer l holds at most one rating per item,
+// so consecutive records of a layer are ratings of distinct items that the kernel can process side by side.
+__global__ void k_layers(const uint64_t *__restrict__ keys_sorted, const int32_t *__restrict__ idx_sorted, int64_t n,
+                         uint8_t *layer /* by original index */) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < n; k += stride) {
+        const uint64_t key = keys_sorted[k];
+        if (k > 0 && keys_sorted[k - 1] == key) continue;  // not the head of its run
+        int64_t len = 1;
+        while (k + len < n && keys_sorted[k + len] == key) ++len;
+        const int64_t chain = len & ~(int64_t)3;
+        for (int64_t j = 0; j < len; ++j) layer[idx_sorted[k + j]] = j < chain ? 0 : (uint8_t)(1 + j - chain);
+    }
+}
+
+// Schedule records streamed by the SGD kernel: {user, slot | (group - 1) << 24, rating bits, ctrl} with
+//   kCtrlDup     user occurs among the previous 15 records of this worker (the kernel prefetches user rows up to
+//                8 ratings ahead and must not prefetch a row it is about to rewrite), or belongs to the
 //                last partial 16-byte chunk of the bias array: such rows are read directly;
 //   kCtrlQuad    records k..k+3 have the same (worker, step, slot) key and none of them is a dup, so
 //                the four users are distinct and the kernel may resolve them as one exact 4-chain;
-//   kCtrlNewStep / kCtrlNewItem   block and item boundaries inside a worker's list.
-//   kCtrlOwn     the user occurs among the previous 15 records OF THIS WORKER: the user's previous rating in
-//                the emitted order is then that record (a user meets a worker in one step only).
+//   kCtrlNewStep / kCtrlNewItem   block and item boundaries inside a worker's list;
+//   kCtrlOwn     the user occurs among the previous 15 records of this worker: the user's previous rating in
+//                the emitted order is then that record (a user meets a worker in one step only);
+//   group        g in 1..4: records k..k+g-1 lie in one (worker, step) block outside the chain parts, have
+//                pairwise distinct items and users and none is a dup -- independent ratings the kernel interleaves.
 // need (nullable): per record, the number of earlier ratings of its user (dataflow schedule); it replaces
 // the step in the low bits of ctrl.
 __global__ void k_build_records(const uint64_t *__restrict__ keys, const int32_t *__restrict__ su,
@@ -150,7 +172,8 @@ __global__ void k_build_records(const uint64_t *__restrict__ keys, const int32_t
                                 int32_t n_users, int4 *rec) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
-    const uint64_t slot_mask = (1ull << kPlanStepShift) - 1;
+    const uint64_t slot_mask = (1ull << kPlanLayerShift) - 1;
+    const uint64_t low_mask = (1ull << kPlanStepShift) - 1;
     for (; k < n; k += stride) {
         const uint64_t key = keys[k];
         auto is_own = [&](int64_t x) {
@@ -173,7 +196,22 @@ __global__ void k_build_records(const uint64_t *__restrict__ keys, const int32_t
         if (!dup && k + 3 < n && keys[k + 1] == key && keys[k + 2] == key && keys[k + 3] == key &&
             !is_dup(k + 1) && !is_dup(k + 2) && !is_dup(k + 3))
             ctrl |= kCtrlQuad;
-        rec[k] = make_int4(su[k], (int32_t)(key & slot_mask), __float_as_int(sr[k]), ctrl);
+        int g = 1;
+        if (!dup && ((key & low_mask) >> kPlanLayerShift) != 0) {
+            const uint64_t blk = key >> kPlanStepShift;
+            uint64_t slots[4] = {key & slot_mask, 0, 0, 0};
+            while (g < 4 && k + g < n) {
+                const uint64_t kg = keys[k + g];
+                if ((kg >> kPlanStepShift) != blk || ((kg & low_mask) >> kPlanLayerShift) == 0 || is_dup(k + g)) break;
+                const uint64_t sg = kg & slot_mask;
+                bool clash = false;
+                for (int j = 0; j < g; ++j) clash |= (slots[j] == sg);
+                if (clash) break;
+                slots[g] = sg;
+                ++g;
+            }
+        }
+        rec[k] = make_int4(su[k], (int32_t)(key & slot_mask) | ((g - 1) << 24), __float_as_int(sr[k]), ctrl);
     }
 }
 

@@ -4,17 +4,18 @@
 #include <stdint.h>
 
 namespace mfk {
-// sort key: [worker | step | slot]
+// sort key: [worker | step | layer | slot]
 constexpr int kPlanWorkerShift = 40;
 constexpr int kPlanStepShift = 24;
+constexpr int kPlanLayerShift = 22;  // inside the low 24 bits: [layer (2) | slot (22)]
 // ctrl word of a schedule record: flags in the high bits; the low bits hold the step (ring schedule, 16 bits) or
-// the number of earlier ratings of the same user in the emitted order (dataflow schedule, 26 bits)
+// the number of earlier ratings of the same user in the emitted order (dataflow schedule, 25 bits)
 constexpr int32_t kCtrlDup = 1 << 30;      // this user occurs among the previous 15 records (do not prefetch its row)
 constexpr int32_t kCtrlQuad = 1 << 29;     // records k..k+3 share worker, step and item, none is kCtrlDup
 constexpr int32_t kCtrlNewStep = 1 << 28;  // first record of a (worker, step) block
 constexpr int32_t kCtrlNewItem = 1 << 27;  // item differs from the previous record of this worker
 constexpr int32_t kCtrlOwn = 1 << 26;      // the user's previous rating is one of this worker's previous 15 records
-constexpr int32_t kNeedMask = (1 << 26) - 1;
+constexpr int32_t kNeedMask = (1 << 25) - 1;
 constexpr int32_t kDefaultSlack = 1;       // stripes per worker when mfk_plan_opts.stripe_slack is 0
 }  // namespace mfk
 

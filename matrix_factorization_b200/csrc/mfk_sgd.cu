@@ -203,10 +203,11 @@ __device__ __forceinline__ void cp_async_wait_dyn(int n) {
     }
 }
 
-// One SGD step on registers.  p, q, ub, ib are updated in place (subject to the flags).
+// One SGD step on registers, in three parts: the per-lane partial of the dot product (squared distance for rbf),
+// the scalar part (error, bias updates, gradient factor) and the row updates.  p, q, ub, ib are updated in place
+// (subject to the flags).
 template <int KERNEL, int NV>
-__device__ __forceinline__ void sgd_step(Row<NV> &p, Row<NV> &q, float &ub, float &ib, float r,
-                                         const SgdParams &prm) {
+__device__ __forceinline__ float sgd_partial(const Row<NV> &p, const Row<NV> &q) {
     float acc = 0.f;
     if (KERNEL == MFK_KERNEL_RBF) {
 #pragma unroll
@@ -227,15 +228,18 @@ __device__ __forceinline__ void sgd_step(Row<NV> &p, Row<NV> &q, float &ub, floa
             acc = fmaf(p.v[j].w, q.v[j].w, acc);
         }
     }
-    acc = warp_sum(acc);
+    return acc;
+}
 
+// returns gp:  p -= lr*(gp*q' + reg*p) with q' = q (linear/sigmoid) or (q - p) (rbf)
+template <int KERNEL>
+__device__ __forceinline__ float sgd_scalar(float acc, float &ub, float &ib, float r, const SgdParams &prm) {
     const float lr = prm.lr, reg = prm.reg;
-    float gp;  // p -= lr*(gp*q' + reg*p) with q' = q (linear/sigmoid) or (q - p) (rbf)
     if (KERNEL == MFK_KERNEL_LINEAR) {
         float err = (prm.mu + ib + ub + acc) - r;  // kernels.py:145-153
         if (prm.upd_user) ub -= lr * (err + reg * ub);
         if (prm.upd_item) ib -= lr * (err + reg * ib);
-        gp = err;
+        return err;
     } else if (KERNEL == MFK_KERNEL_SIGMOID) {
         float x = prm.mu + ub + ib + acc;  // kernels.py:224-234
         float ex = expf(-x);
@@ -244,13 +248,18 @@ __device__ __forceinline__ void sgd_step(Row<NV> &p, Row<NV> &q, float &ub, floa
         float D = (s * s) * ex;  // sigma^2 * e^-x, no factor c
         if (prm.upd_user) ub -= lr * (err * D + reg * ub);
         if (prm.upd_item) ib -= lr * (err * D + reg * ib);
-        gp = err * D;
+        return err * D;
     } else {
         float E = expf(-prm.gamma * acc);  // kernels.py:301-309
         float err = (prm.a + prm.c * E) - r;
         float D = 2.0f * E * prm.gamma;  // no factor c
-        gp = err * D;
+        return err * D;
     }
+}
+
+template <int KERNEL, int NV>
+__device__ __forceinline__ void sgd_apply(Row<NV> &p, Row<NV> &q, float gp, const SgdParams &prm) {
+    const float lr = prm.lr, reg = prm.reg;
     const float decay = 1.0f - lr * reg;
 #pragma unroll
     for (int j = 0; j < NV; ++j) {
@@ -281,6 +290,30 @@ __device__ __forceinline__ void sgd_step(Row<NV> &p, Row<NV> &q, float &ub, floa
         if (prm.upd_user) p.v[j] = pn;
         if (prm.upd_item) q.v[j] = qn;
     }
+}
+
+template <int KERNEL, int NV>
+__device__ __forceinline__ void sgd_step(Row<NV> &p, Row<NV> &q, float &ub, float &ib, float r,
+                                         const SgdParams &prm) {
+    const float acc = warp_sum(sgd_partial<KERNEL, NV>(p, q));
+    const float gp = sgd_scalar<KERNEL>(acc, ub, ib, r, prm);
+    sgd_apply<KERNEL, NV>(p, q, gp, prm);
+}
+
+// Sum each of four per-lane partials over the warp and return the four totals in every lane: recursive halving
+// (2 + 1 + 3 shuffles) and four broadcasts -- the latency of one butterfly reduction for four values.
+__device__ __forceinline__ void reduce4(float (&v)[4], int lane) {
+    const bool b4 = lane & 16, b3 = lane & 8;
+    const float a0 = (b4 ? v[2] : v[0]) + __shfl_xor_sync(0xffffffffu, b4 ? v[0] : v[2], 16);
+    const float a1 = (b4 ? v[3] : v[1]) + __shfl_xor_sync(0xffffffffu, b4 ? v[1] : v[3], 16);
+    float b = (b3 ? a1 : a0) + __shfl_xor_sync(0xffffffffu, b3 ? a0 : a1, 8);
+    b += __shfl_xor_sync(0xffffffffu, b, 4);
+    b += __shfl_xor_sync(0xffffffffu, b, 2);
+    b += __shfl_xor_sync(0xffffffffu, b, 1);
+    v[0] = __shfl_sync(0xffffffffu, b, 0);   // (bit4, bit3) = (0, 0)
+    v[1] = __shfl_sync(0xffffffffu, b, 8);   // (0, 1)
+    v[2] = __shfl_sync(0xffffffffu, b, 16);  // (1, 0)
+    v[3] = __shfl_sync(0xffffffffu, b, 24);  // (1, 1)
 }
 
 __device__ __forceinline__ float dot4(const float4 &a, const float4 &b, float acc) {
@@ -359,6 +392,7 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
     constexpr int NVR = NV > 0 ? NV : 1;
     constexpr bool has_bias = (KERNEL != MFK_KERNEL_RBF);
     constexpr bool kQuads = (KERNEL == MFK_KERNEL_LINEAR) && (NV == 1 || NV == 2);
+    constexpr bool kPar = QSMEM && NV == 1;  // groups of independent ratings are interleaved (item rows in shared memory)
     constexpr uint32_t RS = 128u * NV + 4u;  // ring slot: a full-width row (zero beyond F) + the 16-byte bias chunk
     const int D = rv.depth;                  // power of two, >= 2
     const uint32_t dmask = (uint32_t)D - 1u;
@@ -409,7 +443,7 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
     ring.ahead = rv.slack - 1;
     ring.max_ns = rv.max_sleep_ns;
     const long long clk_start = clock64();
-    int32_t n_quads = 0, n_singles = 0;
+    int32_t n_quads = 0, n_singles = 0, n_par = 0;
 #if MFK_RING_PROFILE
     long long prof[8] = {0, 0, 0, 0, 0, 0, 0, 0};  // 0 step hand-off, 1 prefetch issue, 2 item switch, 3 cp wait,
                                                   // 4 quad math, 5 quad update/store, 6 single, 7 window slide
@@ -533,7 +567,8 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
             if (f_polling) flow_consume();
             // a 4-chain is entered only with all four ratings ready: whether ratings are resolved as a chain or one
             // by one must not depend on timing (the two differ in rounding)
-            const uint32_t head_end = k + ((kQuads && (ctrl & kCtrlQuad) && D >= 4) ? 4u : 1u);
+            const uint32_t head_end =
+                k + ((kQuads && (ctrl & kCtrlQuad) && D >= 4) ? 4u : ((kPar && D >= 4) ? (uint32_t)(rc.y >> 24) + 1u : 1u));
             if (rdy_end < head_end) {
                 // the head record waits for another worker: publish what we owe, then poll with back-off
                 flow_flush();
@@ -598,7 +633,9 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
             }
         }
         PROF_ADD(1);
-        if (first || (ctrl & kCtrlNewItem)) load_q(rc.y);
+        const int32_t slot_k = rc.y & 0xffffff;
+        const uint32_t grp = (kPar && D >= 4) ? (uint32_t)(rc.y >> 24) + 1u : 1u;  // independent ratings starting here
+        if (grp == 1u && (first || (ctrl & kCtrlNewItem) || (kPar && cur_slot != slot_k))) load_q(slot_k);
         first = false;
         PROF_ADD(2);
         const int32_t u = rc.x;
@@ -692,8 +729,71 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
             k += 4u;
             ++n_quads;
             PROF_ADD(5);
+        } else if (kPar && grp > 1u && pf >= k + grp) {
+            // ---- a group of 2..4 independent ratings (distinct users, distinct items): loads, reductions and stores
+            //      are interleaved, so the group costs about the latency of one rating
+            const int4 r1 = srec[(k + 1u) & 63u], r2 = srec[(k + 2u) & 63u], r3 = srec[(k + 3u) & 63u];
+            flush_q();
+            cur_slot = -1;  // no item row is live in registers after this group
+            cp_async_wait_dyn((int)(pf - grp - k));
+            __syncwarp();
+            PROF_ADD(3);
+            const int32_t us[4] = {u, r1.x, r2.x, r3.x};
+            const int32_t sl[4] = {slot_k, r1.y & 0xffffff, r2.y & 0xffffff, r3.y & 0xffffff};
+            const float rr[4] = {__int_as_float(rc.z), __int_as_float(r1.z), __int_as_float(r2.z), __int_as_float(r3.z)};
+            Row<NVR> pp[4];
+            float ubs[4], ibs[4], v4[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                v4[j] = 0.f;
+                ubs[j] = 0.f;
+                ibs[j] = 0.f;
+                pp[j].v[0] = make_float4(0.f, 0.f, 0.f, 0.f);
+                if (j < (int)grp) {
+                    const float *sj = slot_of(k + (uint32_t)j);
+                    pp[j].v[0] = *reinterpret_cast<const float4 *>(sj + lc);
+                    Row<NVR> qj;
+                    load_row<NVR>(qj, sq + (size_t)sl[j] * ld, lane, F);
+                    if (has_bias) ubs[j] = sj[128 * NV + (us[j] & 3)];
+                    ibs[j] = sbi[sl[j]];
+                    v4[j] = sgd_partial<KERNEL, NVR>(pp[j], qj);
+                }
+            }
+            reduce4(v4, lane);
+            PROF_ADD(4);
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+                if (j < (int)grp) {
+                    Row<NVR> qj;
+                    load_row<NVR>(qj, sq + (size_t)sl[j] * ld, lane, F);
+                    const float gp = sgd_scalar<KERNEL>(v4[j], ubs[j], ibs[j], rr[j], prm);
+                    sgd_apply<KERNEL, NVR>(pp[j], qj, gp, prm);
+                    if (prm.upd_user) {
+                        store_row<NVR>(pp[j], prm.P + (size_t)us[j] * ld, lane, F);
+                        if (has_bias) prm.bu[us[j]] = ubs[j];
+                    }
+                    if (prm.upd_item) {
+                        store_row<NVR>(qj, sq + (size_t)sl[j] * ld, lane, F);
+                        if (lane == 0) sbi[sl[j]] = ibs[j];
+                    }
+                }
+            }
+            if (prm.upd_user) {
+                ring.dirty = true;
+                if constexpr (FLOW) {
+                    flow_done(u, ctrl);
+                    flow_done(r1.x, r1.w);
+                    if (grp > 2u) flow_done(r2.x, r2.w);
+                    if (grp > 3u) flow_done(r3.x, r3.w);
+                    flow_flush();
+                }
+            }
+            k += grp;
+            ++n_par;
+            PROF_ADD(5);
         } else {
             // ---- single rating
+            if (kPar && grp > 1u && cur_slot != slot_k) load_q(slot_k);  // (a group that could not be taken as one)
             Row<NVR> p;
             float ub = 0.f;
             if (ctrl & kCtrlDup) {  // recently updated (or last bias chunk): read directly, after our own stores
@@ -750,8 +850,9 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
         rv.stats[4 * (int64_t)w + 2] = n_quads;
         rv.stats[4 * (int64_t)w + 3] = n_singles;
 #if MFK_RING_PROFILE
-        for (int j = 0; j < 8; ++j) rv.prof[8 * (int64_t)w + j] = prof[j];
+        for (int j = 0; j < 7; ++j) rv.prof[8 * (int64_t)w + j] = prof[j];
 #endif
+        rv.prof[8 * (int64_t)w + 7] = n_par;  // groups of four independent ratings
     }
 
     if (QSMEM && prm.upd_item) {

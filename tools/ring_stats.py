@@ -60,7 +60,7 @@ def main():
     for x in order:
         print(x, counts[x], steps_nonempty[x], st[x, 0] / 1e6, st[x, 1] / 1e6, busy[x] / max(1, counts[x]), st[x, 2], st[x, 3])
     prof = plan.last_profile
-    names = ["handoff", "prefetch", "itemswitch", "cpwait", "quadmath", "quadupd", "single", "slide"]
+    names = ["handoff", "prefetch", "itemswitch", "cpwait", "quadmath", "quadupd", "single", "n_par4"]
     if prof.any():
         for x in list(order[:2]) + [np.argsort(counts)[len(counts) // 2]]:
             print("phase Mcyc worker", x, {n: round(float(v) / 1e6, 2) for n, v in zip(names, prof[x])})
@@ -78,7 +78,7 @@ def main():
         hs, hp = plan.hot_stats, plan.hot_profile
         top = np.argsort(-hs[:, 3])[:3]
         print("hot items:", H, "max cycles (M)", hs[:, 0].max() / 1e6, "ratings max", hs[:, 3].max())
-        names = ["handoff", "rowload", "gram", "subst", "sweep", "misc"]
+        names = ["handoff", "owngram", "gramwait", "subst", "sweep", "endwait", "prefetch"]
         for x in top:
             print("hot worker", x, "ratings", hs[x, 3], "batches", hs[x, 2], "Mcyc", hs[x, 0] / 1e6, "blocked", hs[x, 1] / 1e6,
                   {n: round(float(v) / 1e6, 2) for n, v in zip(names, hp[x])},
