@@ -43,6 +43,7 @@
 namespace mfk {
 
 constexpr int kRingDepthMax = 8;
+constexpr uint32_t kDefaultSleepNs = 256;  // cap of the poll back-off while waiting for a neighbour
 
 struct RingView {
     const int4 *rec;  // per rating {user, slot, rating bits, ctrl}; ctrl = step | kCtrl* flags
@@ -871,6 +872,7 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
 }
 
 #include "mfk_sgd_hot.inc"
+#include "mfk_sgd_hot_pipe.inc"
 
 template <int KERNEL, int NV, bool QSMEM>
 static int launch_ring(const mfk_plan *plan, const SgdParams &prm, int depth, size_t smem, cudaStream_t st) {
@@ -895,7 +897,7 @@ static int launch_ring(const mfk_plan *plan, const SgdParams &prm, int depth, si
         }();
         rv.watchdog_ns = wd_ms > 0 ? (unsigned long long)wd_ms * 1000000ull : 0ull;
         const char *e = getenv("MFK_RING_SLEEP_NS");
-        rv.max_sleep_ns = e ? (uint32_t)atoi(e) : 2048u;
+        rv.max_sleep_ns = e ? (uint32_t)atoi(e) : kDefaultSleepNs;
     }
     auto kern = plan->flow ? k_sgd_ring<KERNEL, NV, QSMEM, true> : k_sgd_ring<KERNEL, NV, QSMEM, false>;
     if (plan->flow) MFK_CUDA(cudaMemsetAsync(plan->uver, 0, sizeof(int32_t) * (size_t)plan->n_users, st));
@@ -951,6 +953,15 @@ static int launch_ring_nv(const mfk_plan *plan, const SgdParams &prm, cudaStream
     if (nv == 2) return launch_ring_q<KERNEL, 2>(plan, prm, st);
     if (nv <= 4) return launch_ring_q<KERNEL, 4>(plan, prm, st);
     return launch_ring_q<KERNEL, 8>(plan, prm, st);
+}
+
+// MFK_HOT_PIPE=0 selects the unpipelined hot kernel (diagnostics)
+static bool use_hot_pipe() {
+    static const bool on = [] {
+        const char *e = getenv("MFK_HOT_PIPE");
+        return !(e && atoi(e) == 0);
+    }();
+    return on;
 }
 
 // parameters for a role-swapped sub-plan (its "users" are items and vice versa)
@@ -1027,7 +1038,7 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         SgdParams hp = prm;
         hp.base = next_base(hot, st, &rc);
         if (rc) return rc;
-        if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128) rc = launch_hot<1>(hot, hp, st);
+        if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128) rc = use_hot_pipe() ? launch_hot_pipe<1>(hot, hp, st) : launch_hot<1>(hot, hp, st);
         else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256) rc = launch_hot<2>(hot, hp, st);
         else if (kernel == MFK_KERNEL_LINEAR) rc = launch_ring_nv<MFK_KERNEL_LINEAR>(hot, hp, st);
         else if (kernel == MFK_KERNEL_SIGMOID) rc = launch_ring_nv<MFK_KERNEL_SIGMOID>(hot, hp, st);
@@ -1041,7 +1052,7 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         SgdParams hp = swap_roles(prm, hu);
         hp.base = next_base(hu, st, &rc);
         if (rc) return rc;
-        if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128) rc = launch_hot<1>(hu, hp, st);
+        if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128) rc = use_hot_pipe() ? launch_hot_pipe<1>(hu, hp, st) : launch_hot<1>(hu, hp, st);
         else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256) rc = launch_hot<2>(hu, hp, st);
         else if (kernel == MFK_KERNEL_LINEAR) rc = launch_ring_nv<MFK_KERNEL_LINEAR>(hu, hp, st);
         else if (kernel == MFK_KERNEL_SIGMOID) rc = launch_ring_nv<MFK_KERNEL_SIGMOID>(hu, hp, st);
