@@ -78,7 +78,7 @@ def main():
         hs, hp = plan.hot_stats, plan.hot_profile
         top = np.argsort(-hs[:, 3])[:3]
         print("hot items:", H, "max cycles (M)", hs[:, 0].max() / 1e6, "ratings max", hs[:, 3].max())
-        names = ["t", "solve", "sweep", "sync_A", "fetch", "gram", "sync_B"]
+        names = ["t", "solve", "sweep", "sync_A", "fetch", "gram_mma", "sync_B", "gram_epi"]
         for x in top:
             print("hot worker", x, "ratings", hs[x, 3], "batches", hs[x, 2], "Mcyc", hs[x, 0] / 1e6, "blocked", hs[x, 1] / 1e6,
                   {n: round(float(v) / 1e6, 2) for n, v in zip(names, hp[x])},
