@@ -114,6 +114,9 @@ int mfk_plan_assignment(const mfk_plan *plan, int32_t *d_worker, int32_t *d_step
  * waits, 4-rating chains resolved at once, ratings processed singly}, then [n_workers][8] phase
  * cycle counters that only builds with -DMFK_RING_PROFILE=1 fill in. */
 int mfk_plan_stats(const mfk_plan *plan, int64_t *d_stats, void *stream);
+/* Diagnostics: which phases of a split plan the SGD epoch entry points run (bit 0 hot items, bit 1 hot users,
+ * bit 2 the rest; default 7).  Lets a benchmark time the three kernels of an epoch one by one. */
+int mfk_plan_set_phases(mfk_plan *plan, uint32_t mask);
 
 /* ------------------------------------------------------------------------------------
  * KernelMF.  One epoch of kernel_matrix_factorization.py:374-425 (the rating loop of _sgd,

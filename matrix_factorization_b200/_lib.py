@@ -52,6 +52,7 @@ SIGNATURES = {
     "mfk_plan_order": (_int, [_p, _p, _p]),
     "mfk_plan_assignment": (_int, [_p, _p, _p, _p]),
     "mfk_plan_stats": (_int, [_p, _p, _p]),
+    "mfk_plan_set_phases": (_int, [_p, C.c_uint32]),
     "mfk_kmf_sgd_epoch": (_int, [_p, _int, _p, _p, _p, _p, _i32, _i32, _f32, _f32, _f32, _f32, _f32, _f32, _int,
                                  _int, _p]),
     "mfk_sse_workspace_bytes": (C.c_size_t, []),

@@ -50,6 +50,7 @@ struct mfk_plan {
     // and items exchanged (swapped = 1: su holds item ids, si user ids, the workers own users)
     mfk_plan *hot_users = nullptr;
     int32_t n_hot_users = 0, swapped = 0;
+    uint32_t phases = 7;  // diagnostics: bit 0 hot items, bit 1 hot users, bit 2 the rest (mfk_plan_set_phases)
     int64_t n_total = 0;
     int32_t n_hot_items = 0;
     long long *stats = nullptr;  // [W][4] per-worker counters of the last SGD epoch (diagnostics)

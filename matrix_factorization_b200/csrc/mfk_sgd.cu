@@ -1031,7 +1031,7 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
     prm.upd_user = update_user_params ? 1 : 0;
     prm.upd_item = update_item_params ? 1 : 0;
     int rc;
-    if (plan->hot && plan->hot->n > 0) {
+    if (plan->hot && plan->hot->n > 0 && (plan->phases & 1u)) {
         // hot phase first: the most-rated items, one CTA each (exact mini-batches for the linear kernel; the
         // other kernels walk the same sub-plan with the ring kernel, one warp per item)
         mfk_plan *hot = plan->hot;
@@ -1045,7 +1045,7 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         else rc = launch_ring_nv<MFK_KERNEL_RBF>(hot, hp, st);
         if (rc) return rc;
     }
-    if (plan->hot_users && plan->hot_users->n > 0) {
+    if (plan->hot_users && plan->hot_users->n > 0 && (plan->phases & 2u)) {
         // then the most active users: the update rules are symmetric in (p_u, b_u) <-> (q_i, b_i), so the same
         // kernels run on the role-swapped sub-plan with the parameter arrays exchanged
         mfk_plan *hu = plan->hot_users;
@@ -1059,7 +1059,7 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         else rc = launch_ring_nv<MFK_KERNEL_RBF>(hu, hp, st);
         if (rc) return rc;
     }
-    if (plan->n == 0) return MFK_OK;
+    if (plan->n == 0 || !(plan->phases & 4u)) return MFK_OK;
     prm.base = next_base(plan, st, &rc);
     if (rc) return rc;
     if (kernel == MFK_KERNEL_LINEAR) return launch_ring_nv<MFK_KERNEL_LINEAR>(plan, prm, st);
@@ -1091,21 +1091,21 @@ extern "C" int mfk_bias_sgd_epoch(mfk_plan *plan, float *d_bu, float *d_bi, floa
     prm.upd_user = update_user_params ? 1 : 0;
     prm.upd_item = update_item_params ? 1 : 0;
     int rc;
-    if (plan->hot && plan->hot->n > 0) {
+    if (plan->hot && plan->hot->n > 0 && (plan->phases & 1u)) {
         SgdParams hp = prm;
         hp.base = next_base(plan->hot, st, &rc);
         if (rc) return rc;
         rc = launch_ring_q<MFK_KERNEL_LINEAR, 0>(plan->hot, hp, st);
         if (rc) return rc;
     }
-    if (plan->hot_users && plan->hot_users->n > 0) {
+    if (plan->hot_users && plan->hot_users->n > 0 && (plan->phases & 2u)) {
         SgdParams hp = swap_roles(prm, plan->hot_users);
         hp.base = next_base(plan->hot_users, st, &rc);
         if (rc) return rc;
         rc = launch_ring_q<MFK_KERNEL_LINEAR, 0>(plan->hot_users, hp, st);
         if (rc) return rc;
     }
-    if (plan->n == 0) return MFK_OK;
+    if (plan->n == 0 || !(plan->phases & 4u)) return MFK_OK;
     prm.base = next_base(plan, st, &rc);
     if (rc) return rc;
     return launch_ring_q<MFK_KERNEL_LINEAR, 0>(plan, prm, st);

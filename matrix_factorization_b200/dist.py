@@ -80,7 +80,9 @@ class DsgdTrainer:
             bu_, bi_, br_ = u_local[m].contiguous(), item_local[m].contiguous(), r[m].contiguous()
             self.block_data.append((bu_, bi_, br_))
             self.block_n.append(int(bu_.numel()))
-            self.plans.append(engine.Plan(bu_, bi_, br_, n_users_local, max(1, self.items_per_stripe[j]), n_factors=n_factors))
+            # (hot_min_degree=0: the block's most-rated items / most active users get the exact mini-batch phases)
+            self.plans.append(engine.Plan(bu_, bi_, br_, n_users_local, max(1, self.items_per_stripe[j]), n_factors=n_factors,
+                                          hot_min_degree=0))
         # contiguous Q / bi views the kernel works on (stripe buffers hold [Q | bi] side by side)
         self.Qwork = torch.zeros((self.max_items, ld), dtype=torch.float32, device=device)
         self.biwork = torch.zeros((self.max_items,), dtype=torch.float32, device=device)

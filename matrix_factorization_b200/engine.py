@@ -101,6 +101,10 @@ class Plan:
         check(lib().mfk_plan_assignment(self._h, ptr(w), ptr(s), stream_ptr()))
         return w, s
 
+    def set_phases(self, mask: int = 7):
+        """Diagnostics: run only some phases of a split plan (bit 0 hot items, bit 1 hot users, bit 2 the rest)."""
+        check(lib().mfk_plan_set_phases(self._h, int(mask)))
+
     def stats(self):
         """[n_workers, 4] int64 host array: cycles, blocked cycles, 4-chains, singles of the last epoch."""
         torch = _torch()
