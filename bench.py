@@ -40,7 +40,7 @@ WORKLOADS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (bytes); None = not captured
-KNOWN_DRAM_TRAFFIC = {("ml-20m", "k_sgd_ring"): 316352512 + 609020416}
+KNOWN_DRAM_TRAFFIC = {("ml-20m", "k_sgd_ring"): 322889984 + 611464448}  # profiles/r01b_ncu_full_k_sgd_ring_ml20m.txt
 
 
 def load_peaks():
