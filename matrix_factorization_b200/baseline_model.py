@@ -206,8 +206,10 @@ def _sgd(
     plan.close()
     if update_user_params:
         user_biases[...] = engine.download(bu)
+        _mirror.set_vec(user_biases, bu)  # (re-registers the mirror with the new content fingerprint)
     if update_item_params:
         item_biases[...] = engine.download(bi)
+        _mirror.set_vec(item_biases, bi)
     out = (user_biases, item_biases, train_rmse)
     return out + (order,) if return_order else out
 

@@ -319,9 +319,13 @@ def _sgd(
     if update_user_params:
         user_features[...] = engine.download(P, cols=F)
         user_biases[...] = engine.download(bu)
+        _mirror.set_rows(user_features, P)  # (re-registers the mirror with the new content fingerprint)
+        _mirror.set_vec(user_biases, bu)
     if update_item_params:
         item_features[...] = engine.download(Q, cols=F)
         item_biases[...] = engine.download(bi)
+        _mirror.set_rows(item_features, Q)
+        _mirror.set_vec(item_biases, bi)
     out = (user_features, item_features, user_biases, item_biases, train_rmse)
     return out + (order,) if return_order else out
 

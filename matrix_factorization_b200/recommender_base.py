@@ -234,15 +234,19 @@ class RecommenderBase(BaseEstimator, RegressorMixin, metaclass=ABCMeta):
         return len(self.item_id_map)
 
     def _internal_to_raw_items(self) -> np.ndarray:
+        # The reference rebuilds list(item_id_map.keys()) on every call (recommender_base.py:245).  The cached
+        # array is tied to the dict OBJECT it was built from: every fit() assigns a new item_id_map (same keys, a
+        # different first-appearance order), which must never be served from the previous fit's cache.
         cache = getattr(self, "_raw_items_cache", None)
-        if cache is None or len(cache) != len(self.item_id_map):
+        if cache is None or cache[0] is not self.item_id_map or len(cache[1]) != len(self.item_id_map):
             keys = list(self.item_id_map.keys())
-            cache = np.array(keys) if len(keys) else np.zeros(0, dtype=np.int64)
-            if cache.ndim != 1:  # tuple-like ids
-                cache = np.empty(len(keys), dtype=object)
-                cache[:] = keys
+            arr = np.array(keys) if len(keys) else np.zeros(0, dtype=np.int64)
+            if arr.ndim != 1:  # tuple-like ids
+                arr = np.empty(len(keys), dtype=object)
+                arr[:] = keys
+            cache = (self.item_id_map, arr)
             self._raw_items_cache = cache
-        return cache
+        return cache[1]
 
     def _internal_to_raw_users(self) -> np.ndarray:
         keys = list(self.user_id_map.keys())
