@@ -64,15 +64,20 @@ typedef struct {
     int32_t warps_per_cta; /* 0 = choose */
     int32_t n_factors;     /* hint: n_factors the plan will run with (caps warps_per_cta: rows
                               wider than 256 / 512 floats need 512- / 256-thread CTAs); 0 = unknown */
-    uint32_t hot_min_degree; /* items rated at least this often (at most one per SM) are split off into a "hot"
+    uint32_t hot_min_degree; /* items rated at least this often (at most 32 per SM) are split off into a "hot"
                               sub-plan whose chains a whole CTA resolves as exact mini-batches (linear kernel);
                               0 = default (4096), 0xffffffff = never split */
     uint32_t stripe_slack; /* user stripes per worker (steps per epoch = stripe_slack * n_workers): step s of a
                               worker needs step s - stripe_slack of its ring neighbour, so a worker may run
                               stripe_slack - 1 steps ahead of the hand-off; 0 = default */
-    uint32_t schedule;     /* how the workers synchronise: 0 = default (2), 1 = dataflow -- every rating waits for
-                              exactly the previous rating of its user (per-user version counters), 2 = ring --
-                              workers hand whole user stripes around in lockstep */
+    uint32_t schedule;     /* 0 = default (2).  1 = dataflow -- worker warps, every rating waits for exactly the
+                              previous rating of its user (per-user version counters);
+                              2 = ring -- worker warps hand whole user stripes around in lockstep;
+                              3 = flat (experimental) -- one CTA per worker, the worker's item rows in shared
+                              memory, each (worker, step) cell ordered into batches of ratings with pairwise
+                              distinct users that the CTA applies side by side (needs n_factors in 1..256 and the
+                              item rows of a worker to fit into shared memory; n_workers / warps_per_cta /
+                              stripe_slack left 0; falls back to 2 otherwise) */
     uint32_t no_hot_users; /* 1 = split off hot items only (by default the most active users among the remaining
                               ratings get the same treatment, with the roles of users and items exchanged) */
 } mfk_plan_opts;
@@ -89,8 +94,12 @@ typedef struct {
     int32_t n_steps;       /* R: user stripes == steps per epoch (stripe_slack * n_workers) */
     int64_t n_hot_ratings;
     int32_t n_hot_users;   /* users in the hot-user sub-plan */
-    int32_t reserved;
+    int32_t flat;          /* 1: the main plan is a flat plan (schedule 3) */
     int64_t n_hot_user_ratings;
+    int32_t n_hot_workers;      /* CTAs of the hot-item sub-plan (each owns up to hot_max_slots items) */
+    int32_t n_hot_user_workers; /* CTAs of the hot-user sub-plan */
+    int32_t hot_max_slots;
+    int32_t reserved2;
 } mfk_plan_info;
 
 /* d_u/d_i/d_r: the n ratings as internal ids (0..n_users-1 / 0..n_items-1).  Synchronises
@@ -108,8 +117,8 @@ int mfk_plan_order(const mfk_plan *plan, int64_t *d_order, void *stream);
  * that each (step) wave is conflict-free. */
 int mfk_plan_assignment(const mfk_plan *plan, int32_t *d_worker, int32_t *d_step, void *stream);
 
-/* Diagnostics of the last SGD epoch run on the plan: d_stats is int64[12 * (n_workers + n_hot_items +
- * n_hot_users)] (device; the blocks of the hot-item and the hot-user sub-plan follow the main block, same layout):
+/* Diagnostics of the last SGD epoch run on the plan: d_stats is int64[12 * (n_workers + n_hot_workers +
+ * n_hot_user_workers)] (device; the blocks of the hot-item and the hot-user sub-plan follow the main block, same layout):
  * first [n_workers][4] = {SM cycles from start to last rating, cycles blocked in ring hand-off
  * waits, 4-rating chains resolved at once, ratings processed singly}, then [n_workers][8] phase
  * cycle counters that only builds with -DMFK_RING_PROFILE=1 fill in. */

@@ -32,7 +32,9 @@ class PlanInfo(C.Structure):
                 ("n_ctas", C.c_int32), ("warps_per_cta", C.c_int32), ("max_items_per_worker", C.c_int32),
                 ("max_worker_ratings", C.c_int64), ("max_item_degree", C.c_int64), ("max_user_degree", C.c_int64),
                 ("n_hot_items", C.c_int32), ("n_steps", C.c_int32), ("n_hot_ratings", C.c_int64),
-                ("n_hot_users", C.c_int32), ("reserved", C.c_int32), ("n_hot_user_ratings", C.c_int64)]
+                ("n_hot_users", C.c_int32), ("flat", C.c_int32), ("n_hot_user_ratings", C.c_int64),
+                ("n_hot_workers", C.c_int32), ("n_hot_user_workers", C.c_int32), ("hot_max_slots", C.c_int32),
+                ("reserved2", C.c_int32)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}

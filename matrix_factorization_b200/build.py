@@ -59,7 +59,7 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
         sp = os.path.join(CSRC, src)
         if not force and os.path.exists(obj) and os.path.getmtime(obj) > max(os.path.getmtime(sp), headers_t):
             return obj, ""
-        extra = ["-DMFK_RING_PROFILE=1"] if os.environ.get("MFK_RING_PROFILE") == "1" else []
+        extra = ["-DMFK_RING_PROFILE=1", "-DMFK_BATCH_PROFILE=1"] if os.environ.get("MFK_RING_PROFILE") == "1" else []
         extra += ["-D" + d for d in os.environ.get("MFK_NVCC_DEFS", "").split(",") if d]  # experiments
         cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if ptxas_info else []) + ["-c", sp, "-o", obj]
         if verbose:

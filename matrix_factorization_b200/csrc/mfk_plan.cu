@@ -154,6 +154,79 @@ __global__ void k_layers(const uint64_t *__restrict__ keys_sorted, const int32_t
     }
 }
 
+// rank[original index] = position of the rating inside its run of equal keys (keys sorted; capped at `cap`: the
+// caller checks the maximum against the key layout)
+__global__ void k_run_rank(const uint64_t *__restrict__ keys_sorted, const int32_t *__restrict__ idx_sorted, int64_t n,
+                           int32_t *rank, int32_t *max_rank) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < n; k += stride) {
+        const uint64_t key = keys_sorted[k];
+        if (k > 0 && keys_sorted[k - 1] == key) continue;  // not the head of its run
+        int64_t len = 1;
+        while (k + len < n && keys_sorted[k + len] == key) ++len;
+        for (int64_t j = 0; j < len; ++j) rank[idx_sorted[k + j]] = (int32_t)j;
+        atomicMax(max_rank, (int32_t)(len - 1));
+    }
+}
+
+// flat plans: keys of the three sorting passes
+//   pass 0: [worker | step | slot]  -> rank among the item's ratings in the cell
+//   pass 1: [worker | step | user]  -> rank among the user's ratings in the cell
+//   pass 2: [worker | step | rank_u | rank_i | slot]  -> final order
+__global__ void k_flat_keys(const int32_t *__restrict__ u, const int32_t *__restrict__ i, int64_t n,
+                            const int32_t *__restrict__ ustripe, const int32_t *__restrict__ iworker,
+                            const int32_t *__restrict__ islot, const int32_t *__restrict__ rank_u,
+                            const int32_t *__restrict__ rank_i, int32_t R, int pass, uint64_t *keys, int32_t *idx) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < n; k += stride) {
+        const int32_t ii = i[k], uu = u[k];
+        const int32_t w = iworker[ii];
+        int32_t s = ustripe[uu] - w;  // worker w meets stripe (w + s) mod R at step s
+        if (s < 0) s += R;
+        const uint64_t cell = ((uint64_t)w << kFlatWorkerShift) | ((uint64_t)s << kFlatStepShift);
+        uint64_t low;
+        if (pass == 0) low = (uint64_t)islot[ii];
+        else if (pass == 1) low = (uint64_t)(uint32_t)uu;
+        else low = ((uint64_t)rank_u[k] << kFlatRankUShift) | ((uint64_t)(rank_i[k] >> kFlatRunShift) << kFlatRankIShift) | (uint64_t)islot[ii];
+        keys[k] = cell | low;
+        idx[k] = (int32_t)k;
+    }
+}
+
+// flat plans: gather the rating arrays in final order and build the records the kernel streams:
+//   {user, slot | rank_i << 12 | rank_u << 22, rating bits, step}
+__global__ void k_flat_gather(const uint64_t *__restrict__ keys, const int32_t *__restrict__ idx, int64_t n,
+                              const int32_t *__restrict__ u, const int32_t *__restrict__ i, const float *__restrict__ r,
+                              int32_t *su, int32_t *si, int32_t *sslot, float *sr, int32_t *sstep, int4 *rec) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < n; k += stride) {
+        const uint64_t key = keys[k];
+        const int32_t j = idx[k];
+        const int32_t step = (int32_t)((key >> kFlatStepShift) & 0xffff);
+        su[k] = u[j];
+        si[k] = i[j];
+        sr[k] = r[j];
+        sslot[k] = (int32_t)(key & (kFlatMaxSlots - 1));
+        sstep[k] = step;
+        rec[k] = make_int4(u[j], (int32_t)(uint32_t)(key & 0xffffffffull), __float_as_int(r[j]), step);
+    }
+}
+
+__global__ void k_flat_worker_bounds(const uint64_t *__restrict__ keys, int64_t n, int32_t W, int64_t *wbeg) {
+    int32_t w = blockIdx.x * blockDim.x + threadIdx.x;
+    if (w > W) return;
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((int64_t)(keys[mid] >> kFlatWorkerShift) < (int64_t)w) lo = mid + 1;
+        else hi = mid;
+    }
+    wbeg[w] = lo;
+}
+
 // Schedule records streamed by the SGD kernel: {user, slot | (group - 1) << 24, rating bits, ctrl} with
 //   kCtrlDup     user occurs among the previous 15 records of this worker (the kernel prefetches user rows up to
 //                8 ratings ahead and must not prefetch a row it is about to rewrite), or belongs to the

@@ -1,6 +1,7 @@
 // Internal layout of the opaque mfk_plan handle (see mfk_plan.cu for how it is built).
 #pragma once
 #include <cuda_runtime.h>
+#include <stddef.h>
 #include <stdint.h>
 
 namespace mfk {
@@ -16,6 +17,29 @@ constexpr int32_t kCtrlNewStep = 1 << 28;  // first record of a (worker, step) b
 constexpr int32_t kCtrlNewItem = 1 << 27;  // item differs from the previous record of this worker
 constexpr int32_t kCtrlOwn = 1 << 26;      // the user's previous rating is one of this worker's previous 15 records
 constexpr int32_t kNeedMask = (1 << 25) - 1;
+// "flat" plans (CTA workers, batches of independent ratings, k_sgd_flat): sort key
+//   [worker (16) | step (16) | rank of the rating among its user's ratings in the cell (10) |
+//    (rank among its item's ratings in the cell) >> kFlatRunShift (10) | slot (12)]
+// -- a run of equal (step, rank_u, rank_i >> 2) holds every user once and every item at most four times
+constexpr int kFlatWorkerShift = 48, kFlatStepShift = 32, kFlatRankUShift = 22, kFlatRankIShift = 12;
+constexpr int32_t kFlatMaxSlots = 1 << 12, kFlatMaxRank = 1 << 10;
+constexpr int kFlatRunShift = 2;
+// shared memory of k_sgd_flat<*, NV, B>: nbuf row buffers of B rows, the worker's item rows and biases, per-buffer
+// record fields, flags (B = 64 for rows of up to 128 floats, 32 up to 256)
+inline size_t flat_smem_bytes(int nv, int max_slots, int nbuf) {
+    const size_t fw = 128 * (size_t)nv, b = nv == 1 ? 64 : 32;
+    return 4 * ((size_t)nbuf * b * fw + (size_t)max_slots * (fw + 1) + 4 * (size_t)nbuf * b + 64);
+}
+// row buffers a flat plan can afford (3 preferred, 2 minimum, 0 = the worker's item rows do not fit: no flat plan)
+inline int flat_row_buffers(int n_factors, int max_slots, size_t smem_optin) {
+    const int f4 = (n_factors + 3) & ~3;
+    if (n_factors < 1 || f4 > 256 || max_slots >= kFlatMaxSlots) return 0;
+    const int nv = f4 <= 128 ? 1 : 2;
+    for (int nbuf = 3; nbuf >= 2; --nbuf)
+        if (flat_smem_bytes(nv, max_slots, nbuf) + 1024 <= smem_optin) return nbuf;
+    return 0;
+}
+constexpr int32_t kHotSlotsMax = 32;        // hot ids (items / users) per worker of the batch engine at most
 constexpr int32_t kDefaultSlack = 1;       // stripes per worker when mfk_plan_opts.stripe_slack is 0
 }  // namespace mfk
 
@@ -41,6 +65,7 @@ struct mfk_plan {
     int32_t *iworker = nullptr, *islot = nullptr;  // per item
     int32_t *ustripe = nullptr;                    // per user
     int32_t *flags = nullptr;  // [W] ring progress flags (monotone across epochs)
+    int32_t flat = 0;          // 1: flat plan -- workers are CTAs, records are grouped into conflict-free batches (k_sgd_flat)
     int32_t flow = 0;          // 1: dataflow schedule (records carry the user's version, uver is the live counter)
     int32_t *uver = nullptr;   // [n_users] ratings of each user applied so far in this epoch (dataflow schedule)
     // hot/cold split (optional): `hot` is a plan over the ratings of the most-rated items (one item per

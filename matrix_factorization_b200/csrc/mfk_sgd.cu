@@ -25,6 +25,7 @@
 // (kernels.py:145-178) with one reduction latency per four ratings instead of four.
 #include <algorithm>
 #include <cstdlib>
+#include <cstring>
 
 #include "mfk_common.cuh"
 #include "mfk_plan.h"
@@ -873,6 +874,8 @@ __global__ void __launch_bounds__(ring_max_threads<NV>(), 1) k_sgd_ring(RingView
 
 #include "mfk_sgd_hot.inc"
 #include "mfk_sgd_hot_pipe.inc"
+#include "mfk_sgd_batch.inc"
+#include "mfk_sgd_flat.inc"
 
 template <int KERNEL, int NV, bool QSMEM>
 static int launch_ring(const mfk_plan *plan, const SgdParams &prm, int depth, size_t smem, cudaStream_t st) {
@@ -964,6 +967,20 @@ static bool use_hot_pipe() {
     return on;
 }
 
+// MFK_HOT_ENGINE=legacy selects the round-1 hot kernels (A/B diagnostics)
+static bool use_batch_engine() {
+    static const bool on = [] {
+        const char *e = getenv("MFK_HOT_ENGINE");
+        return !(e && strcmp(e, "legacy") == 0);
+    }();
+    return on;
+}
+// the round-1 kernels rescale by a^-k: keep them away from small or negative a = 1 - lr*reg
+static bool legacy_hot_ok(const SgdParams &prm) {
+    const float a = 1.0f - prm.lr * prm.reg;
+    return a >= 0.5f && a <= 1.0f;
+}
+
 // parameters for a role-swapped sub-plan (its "users" are items and vice versa)
 static SgdParams swap_roles(const SgdParams &prm, const mfk_plan *sub) {
     SgdParams s = prm;
@@ -1038,8 +1055,9 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         SgdParams hp = prm;
         hp.base = next_base(hot, st, &rc);
         if (rc) return rc;
-        if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128) rc = use_hot_pipe() ? launch_hot_pipe<1>(hot, hp, st) : launch_hot<1>(hot, hp, st);
-        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256) rc = launch_hot<2>(hot, hp, st);
+        if (batch_engine_ok(kernel, hp) && use_batch_engine()) rc = launch_batch(hot, hp, st);
+        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128 && hot->max_slots == 1 && legacy_hot_ok(hp)) rc = use_hot_pipe() ? launch_hot_pipe<1>(hot, hp, st) : launch_hot<1>(hot, hp, st);
+        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256 && hot->max_slots == 1 && legacy_hot_ok(hp)) rc = launch_hot<2>(hot, hp, st);
         else if (kernel == MFK_KERNEL_LINEAR) rc = launch_ring_nv<MFK_KERNEL_LINEAR>(hot, hp, st);
         else if (kernel == MFK_KERNEL_SIGMOID) rc = launch_ring_nv<MFK_KERNEL_SIGMOID>(hot, hp, st);
         else rc = launch_ring_nv<MFK_KERNEL_RBF>(hot, hp, st);
@@ -1052,8 +1070,9 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         SgdParams hp = swap_roles(prm, hu);
         hp.base = next_base(hu, st, &rc);
         if (rc) return rc;
-        if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128) rc = use_hot_pipe() ? launch_hot_pipe<1>(hu, hp, st) : launch_hot<1>(hu, hp, st);
-        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256) rc = launch_hot<2>(hu, hp, st);
+        if (batch_engine_ok(kernel, hp) && use_batch_engine()) rc = launch_batch(hu, hp, st);
+        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128 && hu->max_slots == 1 && legacy_hot_ok(hp)) rc = use_hot_pipe() ? launch_hot_pipe<1>(hu, hp, st) : launch_hot<1>(hu, hp, st);
+        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256 && hu->max_slots == 1 && legacy_hot_ok(hp)) rc = launch_hot<2>(hu, hp, st);
         else if (kernel == MFK_KERNEL_LINEAR) rc = launch_ring_nv<MFK_KERNEL_LINEAR>(hu, hp, st);
         else if (kernel == MFK_KERNEL_SIGMOID) rc = launch_ring_nv<MFK_KERNEL_SIGMOID>(hu, hp, st);
         else rc = launch_ring_nv<MFK_KERNEL_RBF>(hu, hp, st);
@@ -1062,6 +1081,11 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
     if (plan->n == 0 || !(plan->phases & 4u)) return MFK_OK;
     prm.base = next_base(plan, st, &rc);
     if (rc) return rc;
+    if (plan->flat) {  // CTA workers, batches of independent ratings
+        if (kernel == MFK_KERNEL_LINEAR) return launch_flat<MFK_KERNEL_LINEAR>(plan, prm, st);
+        if (kernel == MFK_KERNEL_SIGMOID) return launch_flat<MFK_KERNEL_SIGMOID>(plan, prm, st);
+        return launch_flat<MFK_KERNEL_RBF>(plan, prm, st);
+    }
     if (kernel == MFK_KERNEL_LINEAR) return launch_ring_nv<MFK_KERNEL_LINEAR>(plan, prm, st);
     if (kernel == MFK_KERNEL_SIGMOID) return launch_ring_nv<MFK_KERNEL_SIGMOID>(plan, prm, st);
     return launch_ring_nv<MFK_KERNEL_RBF>(plan, prm, st);
@@ -1106,6 +1130,7 @@ extern "C" int mfk_bias_sgd_epoch(mfk_plan *plan, float *d_bu, float *d_bi, floa
         if (rc) return rc;
     }
     if (plan->n == 0 || !(plan->phases & 4u)) return MFK_OK;
+    MFK_REQUIRE(!plan->flat, "mfk_bias_sgd_epoch: the plan was built for factor rows (n_factors > 0); build it with n_factors = 0");
     prm.base = next_base(plan, st, &rc);
     if (rc) return rc;
     return launch_ring_q<MFK_KERNEL_LINEAR, 0>(plan, prm, st);

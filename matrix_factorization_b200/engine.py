@@ -109,7 +109,7 @@ class Plan:
         """[n_workers, 4] int64 host array: cycles, blocked cycles, 4-chains, singles of the last epoch."""
         torch = _torch()
         info = self.info()
-        W, H, HU = info["n_workers"], info["n_hot_items"], info["n_hot_users"]
+        W, H, HU = info["n_workers"], info["n_hot_workers"], info["n_hot_user_workers"]
         out = torch.zeros((12 * (W + H + HU),), dtype=torch.int64, device=device())
         check(lib().mfk_plan_stats(self._h, ptr(out), stream_ptr()))
         out = out.cpu().numpy()

@@ -36,8 +36,8 @@ def main():
                        hot_min_degree=engine.Plan.NO_HOT_SPLIT if args.no_hot else 0)
     info = plan.info()
     w, s = plan.assignment()
-    H = info["n_hot_items"]
-    HH = H + info["n_hot_users"]
+    H = info["n_hot_workers"]
+    HH = H + info["n_hot_user_workers"]
     w, s = w[w >= HH] - HH, s[w >= HH] - HH  # cold workers only (the workers / steps of the hot phases are numbered first)
     counts = torch.bincount(w.long(), minlength=info["n_workers"]).cpu().numpy()
     steps_nonempty = torch.unique(w.long() * 65536 + s.long()).div(65536, rounding_mode="floor").bincount(minlength=info["n_workers"]).cpu().numpy()
@@ -61,6 +61,12 @@ def main():
         print(x, counts[x], steps_nonempty[x], st[x, 0] / 1e6, st[x, 1] / 1e6, busy[x] / max(1, counts[x]), st[x, 2], st[x, 3])
     prof = plan.last_profile
     names = ["handoff", "prefetch", "itemswitch", "cpwait", "quadmath", "quadupd", "single", "n_par4"]
+    if info.get("flat"):
+        names = ["late_batches", "rec_wait", "fetch", "apply_f", "end_wait", "barrier_f", "apply_0", "barrier_0"]
+        x = int(np.argmax(st[:, 0]))
+        print("flat worker", x, "batches", st[x, 2], "ratings", st[x, 3], "Mcyc", st[x, 0] / 1e6, "blocked", st[x, 1] / 1e6,
+              {n: round(float(v) / 1e6, 2) for n, v in zip(names, prof[x])},
+              "cyc/batch", {n: int(v / max(1, st[x, 2])) for n, v in zip(names, prof[x])})
     if prof.any():
         for x in list(order[:2]) + [np.argsort(counts)[len(counts) // 2]]:
             print("phase Mcyc worker", x, {n: round(float(v) / 1e6, 2) for n, v in zip(names, prof[x])})
@@ -78,7 +84,7 @@ def main():
         hs, hp = plan.hot_stats, plan.hot_profile
         top = np.argsort(-hs[:, 3])[:3]
         print("hot items:", H, "max cycles (M)", hs[:, 0].max() / 1e6, "ratings max", hs[:, 3].max())
-        names = ["t", "solve", "sweep", "sync_A", "fetch", "gram_mma", "sync_B", "gram_epi"]
+        names = ["t", "solve", "sums", "sweep", "fetch", "gram", "inverse", "sync_A"]
         for x in top:
             print("hot worker", x, "ratings", hs[x, 3], "batches", hs[x, 2], "Mcyc", hs[x, 0] / 1e6, "blocked", hs[x, 1] / 1e6,
                   {n: round(float(v) / 1e6, 2) for n, v in zip(names, hp[x])},
