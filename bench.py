@@ -213,7 +213,7 @@ def run_ours_single(args):
     torch.cuda.synchronize()
     t0 = time.perf_counter()
     plan = engine.Plan(wl["u"], wl["i"], wl["r"], U, I, n_factors=F, n_workers=args.workers, warps_per_cta=args.warps,
-                       hot_min_degree=engine.Plan.NO_HOT_SPLIT if args.no_hot else 0)
+                       hot_min_degree=engine.Plan.NO_HOT_SPLIT if args.no_hot else args.hot_min_degree)
     torch.cuda.synchronize()
     plan_ms = 1e3 * (time.perf_counter() - t0)
     info = plan.info()
@@ -345,6 +345,7 @@ def main():
     ap.add_argument("--workers", type=int, default=0)
     ap.add_argument("--warps", type=int, default=0)
     ap.add_argument("--no-hot", action="store_true", help="disable the hot-item sub-plan (cooperative exact mini-batches)")
+    ap.add_argument("--hot-min-degree", type=int, default=0, help="degree from which items / users go to the exact mini-batch engine (0 = default)")
     ap.add_argument("--kernel-only", action="store_true", help="skip the e2e host call and the CPU baseline (profiling)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)

@@ -70,14 +70,16 @@ typedef struct {
     uint32_t stripe_slack; /* user stripes per worker (steps per epoch = stripe_slack * n_workers): step s of a
                               worker needs step s - stripe_slack of its ring neighbour, so a worker may run
                               stripe_slack - 1 steps ahead of the hand-off; 0 = default */
-    uint32_t schedule;     /* 0 = default (2).  1 = dataflow -- worker warps, every rating waits for exactly the
-                              previous rating of its user (per-user version counters);
+    uint32_t schedule;     /* 0 = default: 3 where it applies, else 2.
+                              1 = dataflow ring -- worker warps, every rating waits for exactly the previous rating
+                              of its user (per-user version counters in global memory);
                               2 = ring -- worker warps hand whole user stripes around in lockstep;
-                              3 = flat (experimental) -- one CTA per worker, the worker's item rows in shared
-                              memory, each (worker, step) cell ordered into batches of ratings with pairwise
-                              distinct users that the CTA applies side by side (needs n_factors in 1..256 and the
-                              item rows of a worker to fit into shared memory; n_workers / warps_per_cta /
-                              stripe_slack left 0; falls back to 2 otherwise) */
+                              3 = flat -- one CTA per worker, the worker's item rows in shared memory, stripes
+                              handed around the ring of CTAs; inside a (worker, step) cell every rating waits for
+                              the previous rating of its user and of its item only (shared-memory progress
+                              counters).  Needs n_factors in 1..256 and the item rows of a worker to fit into shared
+                              memory (n_workers = CTAs, at most one per SM; 0 = choose), otherwise the plan falls
+                              back to 2.  The default only picks it with n_workers / warps_per_cta left 0 */
     uint32_t no_hot_users; /* 1 = split off hot items only (by default the most active users among the remaining
                               ratings get the same treatment, with the roles of users and items exchanged) */
 } mfk_plan_opts;

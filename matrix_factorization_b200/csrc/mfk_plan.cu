@@ -177,42 +177,89 @@ __global__ void k_run_rank(const uint64_t *__restrict__ keys_sorted, const int32
 __global__ void k_flat_keys(const int32_t *__restrict__ u, const int32_t *__restrict__ i, int64_t n,
                             const int32_t *__restrict__ ustripe, const int32_t *__restrict__ iworker,
                             const int32_t *__restrict__ islot, const int32_t *__restrict__ rank_u,
-                            const int32_t *__restrict__ rank_i, int32_t R, int pass, uint64_t *keys, int32_t *idx) {
+                            const int32_t *__restrict__ rank_i, int32_t R, int32_t slack, int pass, uint64_t *keys, int32_t *idx) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; k < n; k += stride) {
         const int32_t ii = i[k], uu = u[k];
         const int32_t w = iworker[ii];
-        int32_t s = ustripe[uu] - w;  // worker w meets stripe (w + s) mod R at step s
+        int32_t s = ustripe[uu] - slack * w;  // worker w meets stripe (slack * w + s) mod R at step s
         if (s < 0) s += R;
         const uint64_t cell = ((uint64_t)w << kFlatWorkerShift) | ((uint64_t)s << kFlatStepShift);
         uint64_t low;
         if (pass == 0) low = (uint64_t)islot[ii];
         else if (pass == 1) low = (uint64_t)(uint32_t)uu;
-        else low = ((uint64_t)rank_u[k] << kFlatRankUShift) | ((uint64_t)(rank_i[k] >> kFlatRunShift) << kFlatRankIShift) | (uint64_t)islot[ii];
+        else low = ((uint64_t)rank_u[k] << kFlatRankUShift) | ((uint64_t)rank_i[k] << kFlatRankIShift) | (uint64_t)islot[ii];
         keys[k] = cell | low;
         idx[k] = (int32_t)k;
     }
 }
 
-// flat plans: gather the rating arrays in final order and build the records the kernel streams:
-//   {user, slot | rank_i << 12 | rank_u << 22, rating bits, step}
+// flat plans: gather the rating arrays in final order (the records are completed by k_flat_link / k_flat_records)
 __global__ void k_flat_gather(const uint64_t *__restrict__ keys, const int32_t *__restrict__ idx, int64_t n,
                               const int32_t *__restrict__ u, const int32_t *__restrict__ i, const float *__restrict__ r,
-                              int32_t *su, int32_t *si, int32_t *sslot, float *sr, int32_t *sstep, int4 *rec) {
+                              int32_t *su, int32_t *si, int32_t *sslot, float *sr, int32_t *sstep) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; k < n; k += stride) {
         const uint64_t key = keys[k];
         const int32_t j = idx[k];
-        const int32_t step = (int32_t)((key >> kFlatStepShift) & 0xffff);
         su[k] = u[j];
         si[k] = i[j];
         sr[k] = r[j];
         sslot[k] = (int32_t)(key & (kFlatMaxSlots - 1));
-        sstep[k] = step;
-        rec[k] = make_int4(u[j], (int32_t)(uint32_t)(key & 0xffffffffull), __float_as_int(r[j]), step);
+        sstep[k] = (int32_t)((key >> kFlatStepShift) & 0xffff);
     }
+}
+
+// flat plans: keys [cell | id] over the FINAL positions (id = user or slot); a stable sort then lists every id's
+// ratings inside a cell in list order
+__global__ void k_flat_link_keys(const uint64_t *__restrict__ final_keys, const int32_t *__restrict__ ids, int64_t n,
+                                 uint64_t *keys, int32_t *pos) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < n; k += stride) {
+        keys[k] = ((final_keys[k] >> kFlatStepShift) << kFlatStepShift) | (uint64_t)(uint32_t)ids[k];
+        pos[k] = (int32_t)k;
+    }
+}
+// distance (in list positions) to the previous / next rating of the same id in the cell; 0 = none
+__global__ void k_flat_link(const uint64_t *__restrict__ keys_sorted, const int32_t *__restrict__ pos_sorted, int64_t n,
+                            int32_t *dprev, int32_t *dnext /* nullable */, int32_t *max_dist) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < n; k += stride) {
+        const int32_t p = pos_sorted[k];
+        int32_t d = 0;
+        if (k > 0 && keys_sorted[k - 1] == keys_sorted[k]) d = p - pos_sorted[k - 1];
+        dprev[p] = d;
+        if (dnext) dnext[p] = (k + 1 < n && keys_sorted[k + 1] == keys_sorted[k]) ? pos_sorted[k + 1] - p : 0;
+        if (d > 0) atomicMax(max_dist, d);
+    }
+}
+// the records k_sgd_flat streams: {user, rating bits, slot | distance to the item's previous rating << 16,
+//                                  distance to the user's previous rating | distance to the user's next rating << 16}
+__global__ void k_flat_records(const int32_t *__restrict__ su, const float *__restrict__ sr, const int32_t *__restrict__ sslot,
+                               const int32_t *__restrict__ du_prev, const int32_t *__restrict__ du_next,
+                               const int32_t *__restrict__ di_prev, int64_t n, int4 *rec) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < n; k += stride)
+        rec[k] = make_int4(su[k], __float_as_int(sr[k]), sslot[k] | (di_prev[k] << 16), du_prev[k] | (du_next[k] << 16));
+}
+// cbeg[w * (R + 1) + s] = first list position (absolute) of cell (w, s); the entry s = R closes the worker's list
+__global__ void k_flat_cells(const uint64_t *__restrict__ keys, int64_t n, int32_t W, int32_t R, int32_t *cbeg) {
+    int32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= W * (R + 1)) return;
+    const uint64_t w = (uint64_t)(t / (R + 1)), s = (uint64_t)(t % (R + 1));
+    const uint64_t target = (w << 16) | s;  // first key with (worker, step) >= (w, s); s == R rolls over to the next worker
+    int64_t lo = 0, hi = n;
+    while (lo < hi) {
+        int64_t mid = (lo + hi) >> 1;
+        if ((keys[mid] >> kFlatStepShift) < target) lo = mid + 1;
+        else hi = mid;
+    }
+    cbeg[t] = (int32_t)lo;
 }
 
 __global__ void k_flat_worker_bounds(const uint64_t *__restrict__ keys, int64_t n, int32_t W, int64_t *wbeg) {

@@ -19,16 +19,16 @@ constexpr int32_t kCtrlOwn = 1 << 26;      // the user's previous rating is one 
 constexpr int32_t kNeedMask = (1 << 25) - 1;
 // "flat" plans (CTA workers, batches of independent ratings, k_sgd_flat): sort key
 //   [worker (16) | step (16) | rank of the rating among its user's ratings in the cell (10) |
-//    (rank among its item's ratings in the cell) >> kFlatRunShift (10) | slot (12)]
-// -- a run of equal (step, rank_u, rank_i >> 2) holds every user once and every item at most four times
+//    rank among its item's ratings in the cell (10) | slot (12)]
+// -- neighbours in the list are ratings of different users and items wherever the cell allows it
 constexpr int kFlatWorkerShift = 48, kFlatStepShift = 32, kFlatRankUShift = 22, kFlatRankIShift = 12;
 constexpr int32_t kFlatMaxSlots = 1 << 12, kFlatMaxRank = 1 << 10;
-constexpr int kFlatRunShift = 2;
-// shared memory of k_sgd_flat<*, NV, B>: nbuf row buffers of B rows, the worker's item rows and biases, per-buffer
-// record fields, flags (B = 64 for rows of up to 128 floats, 32 up to 256)
+constexpr int32_t kFlatDefaultSlack = 2;  // stripes per worker of a flat plan when mfk_plan_opts.stripe_slack is 0
+// shared memory of k_sgd_flat<*, NV, NBUF>: nbuf row buffers of C rows with their records and user biases, the
+// worker's item rows and biases, control words (C = 64 for rows of up to 128 floats, 32 up to 256)
 inline size_t flat_smem_bytes(int nv, int max_slots, int nbuf) {
-    const size_t fw = 128 * (size_t)nv, b = nv == 1 ? 64 : 32;
-    return 4 * ((size_t)nbuf * b * fw + (size_t)max_slots * (fw + 1) + 4 * (size_t)nbuf * b + 64);
+    const size_t fw = 128 * (size_t)nv, c = nv == 1 ? 64 : 32;
+    return 4 * ((size_t)nbuf * c * (fw + 5) + (size_t)max_slots * (fw + 1) + 4 + 64);
 }
 // row buffers a flat plan can afford (3 preferred, 2 minimum, 0 = the worker's item rows do not fit: no flat plan)
 inline int flat_row_buffers(int n_factors, int max_slots, size_t smem_optin) {
@@ -61,6 +61,7 @@ struct mfk_plan {
     int4 *rec = nullptr;       // {user, slot, rating bits, ctrl}: what the SGD kernel streams
     int32_t *sidx = nullptr;   // index into the arrays given to mfk_plan_create
     int64_t *wbeg = nullptr;   // [W+1] list bounds per worker
+    int32_t *cbeg = nullptr;   // flat plans: [W][R + 1] first list position of every (worker, step) cell
     int32_t *witems = nullptr; // [max_slots][W] item id owned by (slot, worker) or -1
     int32_t *iworker = nullptr, *islot = nullptr;  // per item
     int32_t *ustripe = nullptr;                    // per user

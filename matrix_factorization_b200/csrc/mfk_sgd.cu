@@ -50,6 +50,7 @@ struct RingView {
     const int4 *rec;  // per rating {user, slot, rating bits, ctrl}; ctrl = step | kCtrl* flags
     const int64_t *wbeg;
     const int32_t *witems;
+    const int32_t *cbeg = nullptr;  // flat plans: [W][R + 1] first list position of every (worker, step) cell
     int32_t *flags;
     int32_t W, k, max_slots;
     int32_t R, slack;  // steps per epoch (= stripes = slack * W); step s needs the neighbour's step s - slack

@@ -62,11 +62,11 @@ def main():
     prof = plan.last_profile
     names = ["handoff", "prefetch", "itemswitch", "cpwait", "quadmath", "quadupd", "single", "n_par4"]
     if info.get("flat"):
-        names = ["late_batches", "rec_wait", "fetch", "apply_f", "end_wait", "barrier_f", "apply_0", "barrier_0"]
         x = int(np.argmax(st[:, 0]))
-        print("flat worker", x, "batches", st[x, 2], "ratings", st[x, 3], "Mcyc", st[x, 0] / 1e6, "blocked", st[x, 1] / 1e6,
-              {n: round(float(v) / 1e6, 2) for n, v in zip(names, prof[x])},
-              "cyc/batch", {n: int(v / max(1, st[x, 2])) for n, v in zip(names, prof[x])})
+        print("flat worker", x, "chunks", st[x, 2], "ratings", st[x, 3], "Mcyc", st[x, 0] / 1e6, "ring wait Mcyc", st[x, 1] / 1e6,
+              "consumers 0..3: dependency wait Mcyc", [round(float(v) / 1e6, 2) for v in prof[x][:4]], "producer/row wait Mcyc", [round(float(v) / 1e6, 2) for v in prof[x][4:]],
+              "cycles per rating", st[x, 0] / max(1, st[x, 3]))
+        print("flat workers: Mcyc min/median/max", st[:, 0].min() / 1e6, np.median(st[:, 0]) / 1e6, st[:, 0].max() / 1e6)
     if prof.any():
         for x in list(order[:2]) + [np.argsort(counts)[len(counts) // 2]]:
             print("phase Mcyc worker", x, {n: round(float(v) / 1e6, 2) for n, v in zip(names, prof[x])})
