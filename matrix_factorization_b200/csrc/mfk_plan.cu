@@ -237,15 +237,25 @@ __global__ void k_flat_link(const uint64_t *__restrict__ keys_sorted, const int3
         if (d > 0) atomicMax(max_dist, d);
     }
 }
-// the records k_sgd_flat streams: {user, rating bits, slot | distance to the item's previous rating << 16,
+// the records k_sgd_flat streams: {user, rating bits, slot | ordinal of the rating among the worker's ratings of the item << 12,
 //                                  distance to the user's previous rating | distance to the user's next rating << 16}
 __global__ void k_flat_records(const int32_t *__restrict__ su, const float *__restrict__ sr, const int32_t *__restrict__ sslot,
                                const int32_t *__restrict__ du_prev, const int32_t *__restrict__ du_next,
-                               const int32_t *__restrict__ di_prev, int64_t n, int4 *rec) {
+                               const int32_t *__restrict__ i_ord, int64_t n, int4 *rec) {
     int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
     int64_t stride = (int64_t)gridDim.x * blockDim.x;
     for (; k < n; k += stride)
-        rec[k] = make_int4(su[k], __float_as_int(sr[k]), sslot[k] | (di_prev[k] << 16), du_prev[k] | (du_next[k] << 16));
+        rec[k] = make_int4(su[k], __float_as_int(sr[k]), sslot[k] | (i_ord[k] << 12), du_prev[k] | (du_next[k] << 16));
+}
+// keys [worker | slot] over the final positions: a stable sort lists every item's ratings in the worker's list order
+__global__ void k_flat_item_keys(const uint64_t *__restrict__ final_keys, const int32_t *__restrict__ sslot, int64_t n,
+                                 uint64_t *keys, int32_t *pos) {
+    int64_t k = blockIdx.x * (int64_t)blockDim.x + threadIdx.x;
+    int64_t stride = (int64_t)gridDim.x * blockDim.x;
+    for (; k < n; k += stride) {
+        keys[k] = ((final_keys[k] >> kFlatWorkerShift) << kFlatWorkerShift) | (uint64_t)(uint32_t)sslot[k];
+        pos[k] = (int32_t)k;
+    }
 }
 // cbeg[w * (R + 1) + s] = first list position (absolute) of cell (w, s); the entry s = R closes the worker's list
 __global__ void k_flat_cells(const uint64_t *__restrict__ keys, int64_t n, int32_t W, int32_t R, int32_t *cbeg) {

@@ -28,7 +28,7 @@ constexpr int32_t kFlatDefaultSlack = 2;  // stripes per worker of a flat plan w
 // worker's item rows and biases, control words (C = 64 for rows of up to 128 floats, 32 up to 256)
 inline size_t flat_smem_bytes(int nv, int max_slots, int nbuf) {
     const size_t fw = 128 * (size_t)nv, c = nv == 1 ? 64 : 32;
-    return 4 * ((size_t)nbuf * c * (fw + 5) + (size_t)max_slots * (fw + 1) + 4 + 64);
+    return 4 * ((size_t)nbuf * c * (fw + 5) + (size_t)max_slots * (fw + 2) + 8 + 64);
 }
 // row buffers a flat plan can afford (3 preferred, 2 minimum, 0 = the worker's item rows do not fit: no flat plan)
 inline int flat_row_buffers(int n_factors, int max_slots, size_t smem_optin) {
