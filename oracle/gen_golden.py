@@ -266,6 +266,18 @@ def fit_vectors():
              recs=json.dumps(recs))
 
 
+def split_vectors():
+    """train_update_test_split (utils.py:8-72) under a fixed numpy seed: the row indices of the six frames."""
+    from matrix_factorization import train_update_test_split as ref_split
+
+    df = synth_ratings(60, 40, 1500, seed=5, min_per_user=6)
+    np.random.seed(17)
+    Xi, yi, Xu, yu, Xt, yt = ref_split(df, frac_new_users=0.25)
+    nxt = np.random.random()  # the RNG state after the call is part of the contract (what fit() draws next)
+    np.savez(os.path.join(OUT, "split.npz"), seed=17, frac=0.25, idx_initial=Xi.index.to_numpy(), idx_update=Xu.index.to_numpy(),
+             idx_test=Xt.index.to_numpy(), y_initial=yi.to_numpy(), y_update=yu.to_numpy(), y_test=yt.to_numpy(), next_draw=nxt)
+
+
 if __name__ == "__main__":
     kat_updates()
     replay_vectors()
@@ -273,4 +285,5 @@ if __name__ == "__main__":
     baseline_vectors()
     preprocess_vectors()
     fit_vectors()
+    split_vectors()
     print("golden fixtures written to", OUT)

@@ -137,6 +137,21 @@ def test_train_update_test_split():
     assert list(Xi.columns) == ["user_id", "item_id"] and yi.name == "rating"
 
 
+def test_train_update_test_split_matches_reference_same_seed():
+    """Pinned to the reference's own output (tests/golden/split.npz, written by oracle/gen_golden.py from
+    matrix_factorization/utils.py:8-72): same rows in the same order in all six frames, same RNG consumption."""
+    g = np.load(os.path.join(os.path.dirname(__file__), "golden", "split.npz"))
+    df = synth_ratings(60, 40, 1500, seed=5, min_per_user=6)
+    np.random.seed(int(g["seed"]))
+    Xi, yi, Xu, yu, Xt, yt = mfb.train_update_test_split(df, frac_new_users=float(g["frac"]))
+    assert np.array_equal(Xi.index.to_numpy(), g["idx_initial"])
+    assert np.array_equal(Xu.index.to_numpy(), g["idx_update"])
+    assert np.array_equal(Xt.index.to_numpy(), g["idx_test"])
+    assert np.array_equal(yi.to_numpy(), g["y_initial"]) and np.array_equal(yu.to_numpy(), g["y_update"])
+    assert np.array_equal(yt.to_numpy(), g["y_test"])
+    assert np.random.random() == float(g["next_draw"])
+
+
 def test_synthetic_generator_shapes():
     df = synth_ratings(200, 150, 5000, seed=9, min_per_user=5)
     assert len(df) == 5000 and not df.duplicated(["user_id", "item_id"]).any()
@@ -188,3 +203,57 @@ def test_mirror_detects_in_place_edits():
     _mirror._register(table, big, sentinel)
     big[:: (1 << 20) // (1 << 16)] = 1.0  # large arrays: the strided sample catches bulk re-initialisation
     assert _mirror._lookup(table, big) is None
+
+
+def test_topk_metrics_match_per_user_loop():
+    """evaluation.topk_metrics / holdout_split against a per-user restatement of the reference's evaluate loop
+    (project_template/pipeline/evaluate.py:33-111) on random recommendation lists."""
+    from matrix_factorization_b200 import evaluation as ev
+
+    rng = np.random.default_rng(3)
+    df = synth_ratings(80, 60, 2500, seed=11, min_per_user=4)
+    k, n_test, thr, seed = 7, 3, 4.0, 123
+    train, test = ev.holdout_split(df, n_test, thr, seed)
+    # reference-style split, user by user with one RandomState
+    rs = np.random.RandomState(seed)
+    ref_train, ref_test = {}, {}
+    for u in df["user_id"].unique():
+        hist = df[df["user_id"] == u]
+        if hist.shape[0] <= n_test:
+            continue
+        pos = hist[hist["rating"] >= thr]
+        t = pos.sample(n=n_test, random_state=rs) if pos.shape[0] >= n_test else hist.sort_values("rating", ascending=False).head(n_test)
+        ti = t["item_id"].tolist()
+        tr = hist.loc[~hist["item_id"].isin(ti), "item_id"].tolist()
+        if tr and ti:
+            ref_train[u], ref_test[u] = tr, ti
+    assert {u: g["item_id"].tolist() for u, g in train.groupby("user_id", sort=False)} == ref_train
+    assert {u: g["item_id"].tolist() for u, g in test.groupby("user_id", sort=False)} == ref_test
+
+    class FakeModel:  # random lists that avoid the known items, like recommend_all returns them
+        def contains_user(self, u):
+            return True
+
+        def recommend_all(self, users, amount, items_known):
+            known = items_known.groupby("user_id")["item_id"].apply(set).to_dict()
+            rows = []
+            for u in users:
+                cand = [i for i in rng.permutation(60) + 1 if i not in known.get(u, ())][:amount]
+                rows += [(u, i, rk) for rk, i in enumerate(cand)]
+            return pd.DataFrame(rows, columns=["user_id", "item_id", "rank"])
+
+    model = FakeModel()
+    rec = model.recommend_all(list(ref_train), k, train[["user_id", "item_id"]])
+    res = ev.topk_metrics(rec, test, k)
+    ps, rs_, ns = [], [], []
+    for u in ref_train:
+        items = rec[rec.user_id == u].sort_values("rank")["item_id"].tolist()
+        hit = np.array([1 if i in set(ref_test[u]) else 0 for i in items])
+        ps.append(hit.mean())
+        rs_.append(hit.sum() / max(1, len(set(ref_test[u]))))
+        gains = (2.0 ** hit - 1) / np.log2(np.arange(2, hit.size + 2))
+        ideal = np.sort(hit)[::-1]
+        idcg = np.sum((2.0 ** ideal - 1) / np.log2(np.arange(2, ideal.size + 2)))
+        ns.append(gains.sum() / idcg if idcg > 0 else 0.0)
+    assert res.n_users == len(ref_train)
+    assert abs(res.precision - np.mean(ps)) < 1e-12 and abs(res.recall - np.mean(rs_)) < 1e-12 and abs(res.ndcg - np.mean(ns)) < 1e-12
