@@ -1136,3 +1136,16 @@ extern "C" int mfk_bias_sgd_epoch(mfk_plan *plan, float *d_bu, float *d_bi, floa
     if (rc) return rc;
     return launch_ring_q<MFK_KERNEL_LINEAR, 0>(plan, prm, st);
 }
+
+// diagnostics of profile builds: clock stamps of one iteration of the batch engine (not part of include/mfk.h)
+extern "C" int mfk_debug_trace(long long *h_out, int n) {
+#if MFK_BATCH_PROFILE
+    if (n > 256) n = 256;
+    MFK_CUDA(cudaMemcpyFromSymbol(h_out, g_bt_trace, sizeof(long long) * (size_t)n));
+    return MFK_OK;
+#else
+    (void)h_out;
+    (void)n;
+    return MFK_ERR_UNSUPPORTED;
+#endif
+}

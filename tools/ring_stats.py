@@ -45,7 +45,8 @@ def main():
     for e in range(args.epochs):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         a.record()
-        engine.kmf_sgd_epoch(plan, "linear", P, Q, bu, bi, F, mu, wl["lr"], wl["reg"], 1.0 / F, 0.0, 5.0)
+        engine.kmf_sgd_epoch(plan, "linear", P, Q, bu, bi, F, mu, wl["lr"], wl["reg"], 1.0 / F, 0.0, 5.0,
+                             upd_user=not os.environ.get("NO_UPD_USER"), upd_item=not os.environ.get("NO_UPD_ITEM"))
         b.record()
         torch.cuda.synchronize()
         ms.append(a.elapsed_time(b))
@@ -89,6 +90,18 @@ def main():
             print("hot worker", x, "ratings", hs[x, 3], "batches", hs[x, 2], "Mcyc", hs[x, 0] / 1e6, "blocked", hs[x, 1] / 1e6,
                   {n: round(float(v) / 1e6, 2) for n, v in zip(names, hp[x])},
                   "cyc/batch", {n: int(v / max(1, hs[x, 2])) for n, v in zip(names, hp[x])})
+    # one iteration of hot worker 0, warp by warp (profile builds): clock stamps relative to the earliest one
+    import ctypes
+    from matrix_factorization_b200 import _lib
+    L = _lib.lib()
+    if hasattr(L, "mfk_debug_trace"):
+        buf = np.zeros(256, dtype=np.int64)
+        L.mfk_debug_trace.restype = ctypes.c_int
+        if L.mfk_debug_trace(buf.ctypes.data_as(ctypes.c_void_p), 256) == 0 and buf.any():
+            t = buf.reshape(16, 16)
+            t0 = t[t > 0].min()
+            for wp in range(16):
+                print("trace warp", wp, [int(v - t0) if v > 0 else -1 for v in t[wp, :16]])
 
 
 if __name__ == "__main__":
