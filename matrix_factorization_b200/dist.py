@@ -52,10 +52,14 @@ def subepoch_schedule(G: int):
 
 class DsgdTrainer:
     """Rank-local state of a G-GPU DSGD fit.  Construct on every rank with the ratings of the rank's
-    user stripe (local user ids, GLOBAL item stripe / local item ids)."""
+    user stripe (local user ids, GLOBAL item stripe / local item ids).
+
+    The item stripe a rank currently holds lives in ONE flat buffer `[max_items * ld factors | max_items biases]`, so
+    that the SGD kernel works on it in place (Q and bi are views) and one NCCL send / recv moves it to the ring
+    neighbour; a second buffer receives the incoming stripe."""
 
     def __init__(self, rank: int, world: int, u_local, item_stripe, item_local, r, n_users_local: int,
-                 items_per_stripe, n_factors: int, P, Q_stripe, bu, bi_stripe, device):
+                 items_per_stripe, n_factors: int, P, Q_stripe, bu, bi_stripe, device, hot_min_degree: int = 0):
         import torch
         from . import engine
 
@@ -64,55 +68,67 @@ class DsgdTrainer:
         self.P, self.bu = P, bu
         self.n = int(u_local.numel())
         ld = P.shape[1]
+        self.ld = ld
         self.max_items = int(max(items_per_stripe))
-        # two item-stripe buffers (current + incoming), each [max_items, ld + 1]: factors then bias column
-        self.qbuf = [torch.zeros((self.max_items, ld + 4), dtype=torch.float32, device=device) for _ in range(2)]
-        self.qbuf[0][: Q_stripe.shape[0], :ld].copy_(Q_stripe)
-        self.qbuf[0][: Q_stripe.shape[0], ld].copy_(bi_stripe)
+        M = self.max_items
+        self.qbuf = [torch.zeros((M * (ld + 1),), dtype=torch.float32, device=device) for _ in range(2)]
         self.cur = 0
         self.items_per_stripe = [int(x) for x in items_per_stripe]
-        self.ld = ld
-        # one plan per item stripe (block (rank, j))
-        self.plans, self.block_n = [], []
-        self.block_data = []
+        q, b = self.stripe_views(0)
+        q[: Q_stripe.shape[0]].copy_(Q_stripe)
+        b[: Q_stripe.shape[0]].copy_(bi_stripe)
+        # one plan per item stripe (block (rank, j)); hot_min_degree = 0: the block's longest item / user chains go to the
+        # exact mini-batch phases (threshold chosen per block by the plan builder)
+        self.plans, self.block_n, self.block_data = [], [], []
         for j in range(world):
             m = item_stripe == j
             bu_, bi_, br_ = u_local[m].contiguous(), item_local[m].contiguous(), r[m].contiguous()
-            self.block_data.append((bu_, bi_, br_))
+            self.block_data.append((bu_, bi_, br_, torch.nonzero(m).flatten()))
             self.block_n.append(int(bu_.numel()))
-            # (hot_min_degree=0: the block's most-rated items / most active users get the exact mini-batch phases)
             self.plans.append(engine.Plan(bu_, bi_, br_, n_users_local, max(1, self.items_per_stripe[j]), n_factors=n_factors,
-                                          hot_min_degree=0))
-        # contiguous Q / bi views the kernel works on (stripe buffers hold [Q | bi] side by side)
-        self.Qwork = torch.zeros((self.max_items, ld), dtype=torch.float32, device=device)
-        self.biwork = torch.zeros((self.max_items,), dtype=torch.float32, device=device)
+                                          hot_min_degree=hot_min_degree))
         self.sse = torch.zeros((1,), dtype=torch.float64, device=device)
 
-    def epoch(self, kernel, mu, lr, reg, gamma, lo, hi):
-        """One DSGD epoch: G sub-epochs of (local stratified SGD on one block, ring shift of the item stripe)."""
-        import torch
-        import torch.distributed as dist
+    def stripe_views(self, which: int):
+        """(Q [max_items, ld], bi [max_items]) views of stripe buffer `which`."""
+        M, ld = self.max_items, self.ld
+        buf = self.qbuf[which]
+        return buf[: M * ld].view(M, ld), buf[M * ld:]
+
+    def block_order(self, j: int):
+        """Sequential order of block (rank, j) as positions into the arrays this trainer was built from."""
+        if self.block_n[j] == 0:
+            return self.block_data[j][3]
+        return self.block_data[j][3][self.plans[j].order()]
+
+    def sub_epoch(self, s: int, kernel, mu, lr, reg, gamma, lo, hi):
+        """Local stratified SGD on the block this rank holds in sub-epoch s (item stripe (rank + s) mod G), in place."""
         from . import engine
 
-        G, g, ld = self.G, self.rank, self.ld
-        for s in range(G):
-            j = (g + s) % G
-            buf = self.qbuf[self.cur]
-            nj = self.items_per_stripe[j]
-            if self.block_n[j] > 0:
-                self.Qwork[:nj].copy_(buf[:nj, :ld])
-                self.biwork[:nj].copy_(buf[:nj, ld])
-                engine.kmf_sgd_epoch(self.plans[j], kernel, self.P, self.Qwork, self.bu, self.biwork, self.F, mu, lr,
-                                     reg, gamma, lo, hi)
-                buf[:nj, :ld].copy_(self.Qwork[:nj])
-                buf[:nj, ld].copy_(self.biwork[:nj])
-            if G > 1:
-                nxt = self.qbuf[1 - self.cur]
-                ops = [dist.P2POp(dist.isend, buf, (g - 1) % G), dist.P2POp(dist.irecv, nxt, (g + 1) % G)]
-                for w in dist.batch_isend_irecv(ops):
-                    w.wait()
-                self.cur = 1 - self.cur
-        # after G shifts every stripe is back on its home rank: rank g holds stripe g again
+        j = (self.rank + s) % self.G
+        if self.block_n[j] > 0:
+            q, b = self.stripe_views(self.cur)
+            engine.kmf_sgd_epoch(self.plans[j], kernel, self.P, q, self.bu, b, self.F, mu, lr, reg, gamma, lo, hi)
+        return j
+
+    def shift(self):
+        """Ring shift: the held stripe goes to rank - 1, the next one comes from rank + 1 (one send + one recv)."""
+        import torch.distributed as dist
+
+        G, g = self.G, self.rank
+        if G > 1:
+            ops = [dist.P2POp(dist.isend, self.qbuf[self.cur], (g - 1) % G),
+                   dist.P2POp(dist.irecv, self.qbuf[1 - self.cur], (g + 1) % G)]
+            for w in dist.batch_isend_irecv(ops):
+                w.wait()
+            self.cur = 1 - self.cur
+
+    def epoch(self, kernel, mu, lr, reg, gamma, lo, hi):
+        """One DSGD epoch: G sub-epochs of (local stratified SGD on one block, ring shift of the item stripe).
+        After G shifts every stripe is back on its home rank."""
+        for s in range(self.G):
+            self.sub_epoch(s, kernel, mu, lr, reg, gamma, lo, hi)
+            self.shift()
 
     def sse_epoch(self, kernel, mu, gamma, lo, hi):
         """Sum of squared errors of the rank's ratings: all-gather the item stripes, one SSE pass per block."""
@@ -120,23 +136,20 @@ class DsgdTrainer:
         import torch.distributed as dist
         from . import engine
 
-        G, ld = self.G, self.ld
+        G, ld, M = self.G, self.ld, self.max_items
         mine = self.qbuf[self.cur]
         if G > 1:
-            allq = [torch.empty_like(mine) for _ in range(G)]
-            dist.all_gather(allq, mine)
+            allq = torch.empty((G, M * (ld + 1)), dtype=torch.float32, device=self.device)
+            dist.all_gather_into_tensor(allq.view(-1), mine)
         else:
-            allq = [mine]
+            allq = mine.view(1, -1)
         total = torch.zeros((1,), dtype=torch.float64, device=self.device)
         for j in range(G):
             if self.block_n[j] == 0:
                 continue
-            nj = self.items_per_stripe[j]
-            self.Qwork[:nj].copy_(allq[j][:nj, :ld])
-            self.biwork[:nj].copy_(allq[j][:nj, ld])
-            bu_, bi_, br_ = self.block_data[j]
-            engine.kmf_sse(kernel, bu_, bi_, br_, self.P, self.Qwork, self.bu, self.biwork, self.F, mu, gamma, lo, hi,
-                           self.sse)
+            bu_, bi_, br_, _ = self.block_data[j]
+            engine.kmf_sse(kernel, bu_, bi_, br_, self.P, allq[j][: M * ld].view(M, ld), self.bu, allq[j][M * ld:], self.F, mu,
+                           gamma, lo, hi, self.sse)
             total += self.sse
         if G > 1:
             dist.all_reduce(total)
@@ -144,9 +157,9 @@ class DsgdTrainer:
 
     def home_stripe(self):
         """(Q stripe [n_items_of_stripe, ld], bi stripe) of this rank's home item stripe."""
-        buf = self.qbuf[self.cur]
+        q, b = self.stripe_views(self.cur)
         nj = self.items_per_stripe[self.rank]
-        return buf[:nj, : self.ld], buf[:nj, self.ld]
+        return q[:nj], b[:nj]
 
 
 def sharded_topk(kernel, users, P, bu, Q_local, bi_local, local_to_global, n_factors, mu, gamma, lo, hi, k, bound,

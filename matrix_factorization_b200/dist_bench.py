@@ -112,7 +112,8 @@ def run(args):
             continue
         nj = tr.items_per_stripe[j]
         ka.record()
-        engine.kmf_sgd_epoch(tr.plans[j], "linear", tr.P, tr.Qwork, tr.bu, tr.biwork, F, mu, lr, reg, gamma, 0.0, 5.0)
+        qv, bv = tr.stripe_views(tr.cur)
+        engine.kmf_sgd_epoch(tr.plans[j], "linear", tr.P, qv, tr.bu, bv, F, mu, lr, reg, gamma, 0.0, 5.0)
         kb.record()
         torch.cuda.synchronize()
         kms += ka.elapsed_time(kb)
@@ -161,7 +162,7 @@ def run(args):
                        "plan_build_ms": plan_ms, "l2": "per-rank working set exceeds L2, no explicit flush",
                        "train_rmse_first_last": [rmse[0], rmse[-1]]},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                         "traffic": None, "kernel": "k_sgd_ring (rank 0, its G block launches of one epoch)",
+                         "traffic": None, "kernel": "rank 0: the SGD launches (k_sgd_batch hot items / hot users, k_sgd_flat) of its G blocks of one epoch",
                          "kernel_ms": kms, "bytes_per_update": bpu, "peak_source": peak_src},
             "cpu_baseline": None,
             "e2e": {"value": N * wl["n_epochs"] / e2e_s, "unit": "rating-updates/s",
