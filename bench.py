@@ -27,6 +27,7 @@ import time
 
 ROOT = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, ROOT)
+os.environ.setdefault("ORACLE_FAST", "1")  # the timed CPU arm: gcc -O3 -march=native (same arithmetic, see oracle/oracle.py)
 
 import numpy as np  # noqa: E402
 
@@ -98,6 +99,52 @@ def gen_workload(name, device, uniform=False, seed=None):
     seed = 1000 + list(SHAPES).index(shape) if seed is None else seed
     u, i, r = synth_ratings_torch(U, I, N, seed, device, grid_step=step, uniform=uniform)
     return dict(U=U, I=I, N=N, F=F, n_epochs=n_epochs, lr=lr, reg=reg, u=u, i=i, r=r)
+
+
+def parity_at_scale(n_sample=2_000_000, F=128, seed=1234, U=40_000, I=8_000, data=None):
+    """one epoch of the DEFAULT plan (hot items, hot users, flat phase -- the kernels the timed
+    region runs) replayed through the fp64 oracle in the emitted order.  `data` = (u, i, r) device tensors (bench.py passes
+    the workload itself, or its first 10 M ratings when it is larger); without it a Zipf sample of n_sample ratings is
+    generated.  Returns the largest relative errors; bench.py fails the run above 1e-4."""
+    import torch
+    from matrix_factorization_b200 import engine
+    from matrix_factorization_b200.data import synth_ratings_torch
+    from oracle import oracle as orc
+
+    dev = torch.device("cuda", torch.cuda.current_device())
+    if data is None:
+        u, i, r = synth_ratings_torch(U, I, n_sample, seed, dev, grid_step=0.5)
+    else:
+        u, i, r = data
+        n_sample = int(u.numel())
+    g = torch.Generator(device=dev).manual_seed(seed)
+    P = torch.randn(U, F, device=dev, generator=g) * 0.1
+    Q = torch.randn(I, F, device=dev, generator=g) * 0.1
+    bu, bi = torch.zeros(U, device=dev), torch.zeros(I, device=dev)
+    P0, Q0 = P.double().cpu().numpy(), Q.double().cpu().numpy()
+    mu = float(r.double().mean().item())
+    plan = engine.Plan(u, i, r, U, I, n_factors=F, hot_min_degree=0)
+    info = plan.info()
+    lr, reg = 0.001, 0.005
+    engine.kmf_sgd_epoch(plan, "linear", P, Q, bu, bi, F, mu, lr, reg, 1.0 / F, 0.0, 5.0)
+    order = plan.order().cpu().numpy()
+    t0 = time.perf_counter()
+    Po, Qo, buo, bio = orc.kmf_replay("linear", u.cpu().numpy(), i.cpu().numpy(), r.double().cpu().numpy(), order, mu,
+                                      np.zeros(U), np.zeros(I), P0, Q0, lr, reg)
+    dt = time.perf_counter() - t0
+    rel = lambda a, b: float(np.max(np.abs(a - b)) / max(1e-30, np.max(np.abs(b))))
+    # the update of one epoch is small next to the factors: also compare the CHANGE each side made
+    dP, dQ = P.double().cpu().numpy() - P0, Q.double().cpu().numpy() - Q0
+    out = {"ratings": int(n_sample), "n_factors": F, "users": U, "items": I,
+           "hot_items": info["n_hot_items"], "hot_ratings": info["n_hot_ratings"], "hot_users": info["n_hot_users"],
+           "hot_user_ratings": info["n_hot_user_ratings"],
+           "rel_err_P": rel(P.double().cpu().numpy(), Po), "rel_err_Q": rel(Q.double().cpu().numpy(), Qo),
+           "rel_err_update_P": rel(dP, Po - P0), "rel_err_update_Q": rel(dQ, Qo - Q0),
+           "max_abs_err_bu": float(np.max(np.abs(bu.cpu().numpy() - buo))), "max_abs_err_bi": float(np.max(np.abs(bi.cpu().numpy() - bio))),
+           "oracle_replay_s": dt, "tolerance": 1e-4}
+    out["ok"] = bool(out["rel_err_P"] < 1e-4 and out["rel_err_Q"] < 1e-4 and out["max_abs_err_bu"] < 1e-4 and out["max_abs_err_bi"] < 1e-4)
+    plan.close()
+    return out
 
 
 def cpu_baseline(wl, sample_ratings, seed=7):
@@ -253,9 +300,8 @@ def run_ours_single(args):
     # diagnostic pass (outside the timed region): the three kernels of an epoch, one by one
     phases = []
     n_phase = [info["n_hot_ratings"], info["n_hot_user_ratings"], N - info["n_hot_ratings"] - info["n_hot_user_ratings"]]
-    names = ["k_sgd_hot_pipe (hot items)", "k_sgd_hot_pipe (hot users, roles swapped)", "k_sgd_ring (the rest)"]
-    if F > 128:
-        names[0], names[1] = "k_sgd_hot (hot items)", "k_sgd_hot (hot users, roles swapped)"
+    names = ["k_sgd_batch (hot items)", "k_sgd_batch (hot users, roles swapped)",
+             "k_sgd_flat (the rest)" if info.get("flat") else "k_sgd_ring (the rest)"]
     for bit in range(3):
         if n_phase[bit] == 0:
             continue
@@ -283,10 +329,18 @@ def run_ours_single(args):
         ph["exceeds_hbm_peak"] = ph["frac_algorithmic"] > 1.0
     dominant = max(phases, key=lambda ph: ph["ms"])["kernel"] if phases else "k_sgd_ring"
     n_sgd_kernels = max(1, len(phases))
+    parity = None
     if args.kernel_only:  # profiling runs (ncu): skip the host-call and CPU legs
         e2e_v, e2e_dt, h2d, d2h, e2e_rmse = float("nan"), float("nan"), 0, 0, [float("nan")]
         cpu_v, cpu_dt, cpu_n = float("nan"), 0.0, 0
     else:
+        n_par = min(N, 10_000_000 if F > 128 else 25_000_000)  # (the oracle replays ~2.4 M ratings/s at F = 128)
+        parity = parity_at_scale(F=F, U=U, I=I, data=(wl["u"][:n_par].contiguous(), wl["i"][:n_par].contiguous(),
+                                                      wl["r"][:n_par].contiguous()))
+        parity["sample"] = "the whole workload" if n_par == N else f"the first {n_par} ratings of the workload"
+        if not parity["ok"]:
+            print(json.dumps({"error": "parity check at scale failed", "parity": parity}))
+            sys.exit(1)
         e2e_v, e2e_dt, h2d, d2h, e2e_rmse = e2e_host_call(wl, wl["n_epochs"])
         cpu_v, cpu_dt, cpu_n = cpu_baseline(wl, 2_000_000 if F <= 128 else 1_000_000)
     # second half of the headline metric: recommend users/s (top-50 with known-item exclusion) on the same shape
@@ -330,6 +384,7 @@ def run_ours_single(args):
         "gpu_launches": (2 * n_sgd_kernels + 1) * args.steps,  # SGD kernels + one k_sse per rating segment + k_sse_final
         "clocks": clk,
         "recommend": recommend,
+        "parity": parity,
     }
     print(json.dumps(line))
 

@@ -71,7 +71,8 @@ class DsgdTrainer:
         self.ld = ld
         self.max_items = int(max(items_per_stripe))
         M = self.max_items
-        self.qbuf = [torch.zeros((M * (ld + 1),), dtype=torch.float32, device=device) for _ in range(2)]
+        self.buf_len = (M * (ld + 1) + 3) & ~3  # (a multiple of 16 bytes: gathered stripes stay aligned)
+        self.qbuf = [torch.zeros((self.buf_len,), dtype=torch.float32, device=device) for _ in range(2)]
         self.cur = 0
         self.items_per_stripe = [int(x) for x in items_per_stripe]
         q, b = self.stripe_views(0)
@@ -93,7 +94,7 @@ class DsgdTrainer:
         """(Q [max_items, ld], bi [max_items]) views of stripe buffer `which`."""
         M, ld = self.max_items, self.ld
         buf = self.qbuf[which]
-        return buf[: M * ld].view(M, ld), buf[M * ld:]
+        return buf[: M * ld].view(M, ld), buf[M * ld: M * ld + M]
 
     def block_order(self, j: int):
         """Sequential order of block (rank, j) as positions into the arrays this trainer was built from."""
@@ -139,7 +140,7 @@ class DsgdTrainer:
         G, ld, M = self.G, self.ld, self.max_items
         mine = self.qbuf[self.cur]
         if G > 1:
-            allq = torch.empty((G, M * (ld + 1)), dtype=torch.float32, device=self.device)
+            allq = torch.empty((G, self.buf_len), dtype=torch.float32, device=self.device)
             dist.all_gather_into_tensor(allq.view(-1), mine)
         else:
             allq = mine.view(1, -1)
@@ -148,7 +149,7 @@ class DsgdTrainer:
             if self.block_n[j] == 0:
                 continue
             bu_, bi_, br_, _ = self.block_data[j]
-            engine.kmf_sse(kernel, bu_, bi_, br_, self.P, allq[j][: M * ld].view(M, ld), self.bu, allq[j][M * ld:], self.F, mu,
+            engine.kmf_sse(kernel, bu_, bi_, br_, self.P, allq[j][: M * ld].view(M, ld), self.bu, allq[j][M * ld: M * ld + M], self.F, mu,
                            gamma, lo, hi, self.sse)
             total += self.sse
         if G > 1:

@@ -30,13 +30,22 @@ _c = ctypes
 
 
 def build(force: bool = False) -> str:
-    """Compile liboracle.so with gcc (seconds)."""
-    so = os.path.join(_HERE, "liboracle.so")
+    """Compile liboracle.so with gcc (seconds).  ORACLE_FAST=1 (bench.py's CPU arm) builds liboracle_fast.so with
+    -O3 -march=native instead; floating-point contraction and fast-math stay off, so the arithmetic is the same."""
+    fast = os.environ.get("ORACLE_FAST") == "1"
+    name = "liboracle.so"
+    if fast:  # -march=native code must not travel to another CPU: the file name carries the host CPU's signature
+        import hashlib
+        try:
+            sig = "".join(l for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags")))[:20000]
+        except OSError:
+            sig = "unknown"
+        name = "liboracle_fast_%s.so" % hashlib.sha1(sig.encode()).hexdigest()[:10]
+    so = os.path.join(_HERE, name)
     src = os.path.join(_HERE, "mf_oracle.c")
     if force or not os.path.exists(so) or os.path.getmtime(so) < os.path.getmtime(src):
-        subprocess.check_call(
-            ["gcc", "-O2", "-fPIC", "-std=c11", "-fno-fast-math", "-shared", "-o", so, src, "-lm"]
-        )
+        opt = ["-O3", "-march=native", "-ffp-contract=off"] if fast else ["-O2"]
+        subprocess.check_call(["gcc"] + opt + ["-fPIC", "-std=c11", "-fno-fast-math", "-shared", "-o", so, src, "-lm"])
     return so
 
 
