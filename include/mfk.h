@@ -216,6 +216,20 @@ int mfk_topk_merge(const float *d_scores_in, const int32_t *d_items_in, int64_t 
                    void *stream);
 
 /* ------------------------------------------------------------------------------------
+ * Preprocessing on the GPU -- replaces the id-mapping part of RecommenderBase._preprocess_data for integer raw ids
+ * (recommender_base.py:125-164): first-appearance internal ids on the shuffled rows, duplicate check.
+ *
+ * mfk_first_appearance: shuffled[k] = d_raw[d_perm[k]] (d_perm NULL: identity); d_internal[k] = rank of shuffled[k] among
+ * the distinct ids ordered by first occurrence (what `{id: index}` built by a loop over the shuffled rows gives,
+ * :133-140); d_unique[r] = the id of rank r (capacity n); *h_n_unique = number of distinct ids.  Allocates its scratch
+ * internally and synchronises the stream.
+ * mfk_has_duplicate_pairs: *h_flag = 1 if some (d_u[k], d_i[k]) occurs more than once (:127-128). */
+int mfk_first_appearance(const int64_t *d_raw, const int64_t *d_perm, int64_t n, int32_t *d_internal, int64_t *d_unique,
+                         int32_t *h_n_unique, void *stream);
+int mfk_has_duplicate_pairs(const int32_t *d_u, const int32_t *d_i, int64_t n, int64_t n_items, int32_t *h_flag,
+                            void *stream);
+
+/* ------------------------------------------------------------------------------------
  * Host-buffer entry points (what a cgo / JNI / ctypes binding without torch would call).
  * All pointers are HOST pointers; the call allocates device memory, copies in, runs, copies
  * back and synchronises before returning.

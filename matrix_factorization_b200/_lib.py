@@ -73,6 +73,8 @@ SIGNATURES = {
     "mfk_score_topk": (_int, [_int, _p, _i64, _p, _p, _p, _p, _i32, _i32, _i32, _f32, _f32, _f32, _f32, _p, _p, _i32,
                               _int, _p, _p, _p, _p]),
     "mfk_topk_merge": (_int, [_p, _p, _i64, _i32, _i32, _int, _f32, _f32, _p, _p, _p]),
+    "mfk_first_appearance": (_int, [_p, _p, _i64, _p, _p, _p, _p]),
+    "mfk_has_duplicate_pairs": (_int, [_p, _p, _i64, _i64, _p, _p]),
     "mfk_kmf_sgd_host": (_int, [_int, _p, _p, _p, _i64, _i32, _i32, _p, _p, _p, _p, _i32, _i32, _f32, _i32, _f32,
                                 _f32, _f32, _f32, _f32, _int, _int, C.POINTER(PlanOpts), _p, _p]),
     "mfk_bias_sgd_host": (_int, [_p, _p, _p, _i64, _i32, _i32, _p, _p, _f32, _i32, _f32, _f32, _int, _int,

@@ -19,7 +19,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 INCLUDE = os.path.join(os.path.dirname(HERE), "include")
 LIB = os.path.join(CSRC, "libmfk_b200.so")
-SOURCES = ["mfk_plan.cu", "mfk_sgd.cu", "mfk_eval.cu", "mfk_als.cu", "mfk_score.cu", "mfk_score_tc.cu", "mfk_host.cu"]
+SOURCES = ["mfk_plan.cu", "mfk_sgd.cu", "mfk_eval.cu", "mfk_als.cu", "mfk_score.cu", "mfk_score_tc.cu", "mfk_host.cu", "mfk_prep.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ARCH + ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC",
                      "--expt-relaxed-constexpr", "-I", INCLUDE]

@@ -50,6 +50,33 @@ def _has_duplicate_pairs(ucodes: np.ndarray, icodes: np.ndarray, n_items: int) -
     return bool((key[1:] == key[:-1]).any())
 
 
+GPU_PREPROCESS_MIN_ROWS = 2_000_000
+
+
+def _gpu_preprocess_wanted(users: np.ndarray, items: np.ndarray, n: int) -> bool:
+    """The GPU id-mapping path serves integer raw ids from GPU_PREPROCESS_MIN_ROWS rows on (below that the host path is
+    faster than the transfers); MFB_GPU_PREPROCESS=1 / 0 forces / forbids it."""
+    import os
+
+    env = os.environ.get("MFB_GPU_PREPROCESS")
+    if env == "0" or n == 0:
+        return False
+    if users.dtype.kind not in "iu" or items.dtype.kind not in "iu" or users.dtype.itemsize > 8:
+        return False
+    if users.dtype == np.uint64 or items.dtype == np.uint64:
+        return False
+    if env == "1":
+        return True
+    if n < GPU_PREPROCESS_MIN_ROWS:
+        return False
+    from . import engine
+
+    try:
+        return bool(engine._torch().cuda.is_available())
+    except Exception:
+        return False
+
+
 class RecommenderBase(BaseEstimator, RegressorMixin, metaclass=ABCMeta):
     """
     Abstract base of the recommenders (reference: recommender_base.py:14-95).
@@ -98,6 +125,9 @@ class RecommenderBase(BaseEstimator, RegressorMixin, metaclass=ABCMeta):
         items = X["item_id"].to_numpy()
         ratings = X["rating"].to_numpy() if type != "predict" else None
         n = len(users)
+
+        if type == "fit" and _gpu_preprocess_wanted(users, items, n):
+            return self._preprocess_fit_gpu(users, items, ratings)
 
         if type in ("fit", "update"):
             ucodes0, uuniq0 = pd.factorize(users)
@@ -153,6 +183,42 @@ class RecommenderBase(BaseEstimator, RegressorMixin, metaclass=ABCMeta):
         uint = np.array([umap.get(k, -1) for k in uuniq.tolist()] + [-1], dtype=np.int64)
         iint = np.array([imap.get(k, -1) for k in iuniq.tolist()] + [-1], dtype=np.int64)
         return {"u": uint[ucodes], "i": iint[icodes], "r": None}  # code -1 (NaN id) hits the sentinel
+
+    def _preprocess_fit_gpu(self, users: np.ndarray, items: np.ndarray, ratings: np.ndarray) -> dict:
+        """type='fit' for integer raw ids on the GPU: the shuffle permutation is drawn on the host
+        from numpy's global RNG exactly like the reference (:131), the first-appearance id assignment (:133-140) and the
+        duplicate check (:125-128) run in mfk_first_appearance / mfk_has_duplicate_pairs.  Bit-exact with the host path."""
+        import ctypes as C
+
+        from . import engine
+        from ._lib import check, lib, ptr, stream_ptr
+
+        torch = engine._torch()
+        n = len(users)
+        dev = engine.device()
+        d_users = torch.from_numpy(np.array(users, dtype=np.int64, copy=True)).to(dev)
+        d_items = torch.from_numpy(np.array(items, dtype=np.int64, copy=True)).to(dev)
+        # duplicates do not depend on the order: check before the RNG is touched, like the reference (:127 precedes :131)
+        ui = torch.empty((n,), dtype=torch.int32, device=dev)
+        ii = torch.empty((n,), dtype=torch.int32, device=dev)
+        uq = torch.empty((n,), dtype=torch.int64, device=dev)
+        iq = torch.empty((n,), dtype=torch.int64, device=dev)
+        nu, ni, dup = C.c_int32(0), C.c_int32(0), C.c_int32(0)
+        check(lib().mfk_first_appearance(ptr(d_users), None, n, ptr(ui), ptr(uq), C.byref(nu), stream_ptr()))
+        check(lib().mfk_first_appearance(ptr(d_items), None, n, ptr(ii), ptr(iq), C.byref(ni), stream_ptr()))
+        check(lib().mfk_has_duplicate_pairs(ptr(ui), ptr(ii), n, max(1, ni.value), C.byref(dup), stream_ptr()))
+        if dup.value:
+            raise ValueError("Duplicate user-item ratings in matrix")
+        perm = np.random.choice(n, size=n, replace=False)
+        d_perm = torch.from_numpy(perm.astype(np.int64, copy=False)).to(dev)
+        check(lib().mfk_first_appearance(ptr(d_users), ptr(d_perm), n, ptr(ui), ptr(uq), C.byref(nu), stream_ptr()))
+        check(lib().mfk_first_appearance(ptr(d_items), ptr(d_perm), n, ptr(ii), ptr(iq), C.byref(ni), stream_ptr()))
+        user_ids = uq[: nu.value].cpu().numpy()
+        item_ids = iq[: ni.value].cpu().numpy()
+        self.user_id_map = {k: j for j, k in enumerate(user_ids.tolist())}
+        self.item_id_map = {k: j for j, k in enumerate(item_ids.tolist())}
+        self.n_users, self.n_items = len(user_ids), len(item_ids)
+        return {"u": ui.cpu().numpy().astype(np.int64), "i": ii.cpu().numpy().astype(np.int64), "r": ratings[perm]}
 
     def _preprocess_data(
         self, X: pd.DataFrame, y: pd.Series = None, type: str = "fit"
@@ -229,6 +295,13 @@ class RecommenderBase(BaseEstimator, RegressorMixin, metaclass=ABCMeta):
         if not include_user:
             out.drop(["user_id"], axis="columns", inplace=True)
         return out
+
+    def predictor(self, capacity: int = 1024, bound_ratings: bool = True):
+        """Low-latency predictor for small requests (one user x a few hundred items, project_template/app/api.py:43-52):
+        parameters captured on the device, one CUDA-graph replay per request.  See serving.Predictor."""
+        from .serving import Predictor
+
+        return Predictor(self, capacity=capacity, bound_ratings=bound_ratings)
 
     def n_items_total(self) -> int:
         return len(self.item_id_map)
