@@ -18,6 +18,7 @@ def main():
     ap.add_argument("--phases", type=int, default=1)
     ap.add_argument("--epochs", type=int, default=2)
     ap.add_argument("--hot-min-degree", type=int, default=0)
+    ap.add_argument("--slack", type=int, default=0)
     args = ap.parse_args()
     dev = torch.device("cuda", 0)
     wl = bench.gen_workload(args.workload, dev)
@@ -27,7 +28,7 @@ def main():
     Q = torch.randn(I, F, device=dev, generator=g) * 0.1
     bu, bi = torch.zeros(U, device=dev), torch.zeros(I, device=dev)
     mu = float(wl["r"].double().mean().item())
-    plan = engine.Plan(wl["u"], wl["i"], wl["r"], U, I, n_factors=F, hot_min_degree=args.hot_min_degree)
+    plan = engine.Plan(wl["u"], wl["i"], wl["r"], U, I, n_factors=F, hot_min_degree=args.hot_min_degree, stripe_slack=args.slack)
     plan.set_phases(args.phases)
     for _ in range(args.epochs):
         a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
