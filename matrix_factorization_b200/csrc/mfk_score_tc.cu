@@ -9,10 +9,14 @@
 //   warp 0      TMA producer: per k-block of 32 floats loads {U_hi, U_lo, Q_hi, Q_lo} tiles (4 x 16 KB) into a
 //               2-stage shared-memory ring, completion on `full` mbarriers;
 //   warp 1      TMEM allocator + MMA issuer: per k-block 4 x 3 tcgen05.mma.kind::tf32 (M=128, N=128, K=8) into one of
-//               two TMEM accumulators, tcgen05.commit releases the stage / publishes the accumulator;
+//               four TMEM accumulators (all 512 columns), tcgen05.commit releases the stage / publishes the accumulator;
 //   warps 2..5  epilogue: tcgen05.ld of the thread's row (one user per thread), key = alpha*acc + beta[item],
 //               known-item mask by a cursor over the user's sorted list, threshold test against the row's current
-//               k-th best, sorted insertion of the survivors into the row's top-k list in shared memory.
+//               k-th best; the survivors are PARKED in the row's small buffer and the four warps drain their buffers
+//               together at a tile boundary (replace-minimum into the row's unsorted top-k list in shared memory) --
+//               a row gains an entry only ~k ln(n/k) times per pass, but some row of a warp does in almost every chunk,
+//               so inserting on the spot would make the whole warp (and, through the per-tile barrier, all four) pay
+//               the scan for each one.
 #include <cuda.h>
 
 #include <cstdint>
@@ -26,6 +30,8 @@ constexpr int TC_BM = 128, TC_BN = 128, TC_BK = 32, TC_STAGES = 2, TC_KCAP = 64;
 constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;        // 16 KB
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;       // U_hi, U_lo, Q_hi, Q_lo
 constexpr int TC_THREADS = 192;
+constexpr int TC_ACC = 4;                               // TMEM accumulators (4 x 128 columns = all of tensor memory): the MMAs run up to three tiles ahead of the epilogue
+constexpr int TC_CAP = 32;                              // parked survivors per row before the warp drains its buffers
 constexpr int TC_USER_CHUNK = 128 * 256;                // users per workspace chunk
 
 struct TcParams {
@@ -164,10 +170,11 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
     // per-row top-k buffer: composite (sortable score key << 32 | ~item) -- larger = better, unique
     unsigned long long *tk = reinterpret_cast<unsigned long long *>(base + TC_STAGES * TC_STAGE_BYTES);  // [KCAP][128]
     float *sbeta = reinterpret_cast<float *>(tk + TC_KCAP * TC_BM);                                       // [2][128]
-    float *sscr = sbeta + 2 * TC_BN;                                                       // [32][128] survivor scratch
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sscr + 32 * TC_BM);
-    uint64_t *full = bars, *empty = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + 2;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + 2);
+    unsigned long long *sbuf = reinterpret_cast<unsigned long long *>(sbeta + 2 * TC_BN);  // [TC_CAP][128] parked survivors per row
+    uint64_t *bars = reinterpret_cast<uint64_t *>(sbuf + TC_CAP * TC_BM);
+    uint64_t *full = bars, *empty = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + TC_ACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + TC_ACC);
+    volatile uint32_t *s_req = tmem_slot + 1;  // [3] "some epilogue warp wants a drain", one flag per tile (mod 3)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int32_t m0 = blockIdx.x * TC_BM;
@@ -179,18 +186,19 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
         }
-        for (int a = 0; a < 2; ++a) {
+        for (int a = 0; a < TC_ACC; ++a) {
             mbar_init(acc_full + a, 1);
             mbar_init(acc_empty + a, 128);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 1) {  // TMEM: two 128-column fp32 accumulators
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(256u)
+    if (warp == 1) {  // TMEM: TC_ACC 128-column fp32 accumulators
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"((uint32_t)(TC_ACC * TC_BN))
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int j = threadIdx.x; j < TC_KCAP * TC_BM; j += TC_THREADS) tk[j] = 0ull;
+    if (threadIdx.x < 3) s_req[threadIdx.x] = 0u;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -224,8 +232,8 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                                    ((uint32_t)(TC_BM >> 4) << 24);
             uint32_t stage = 0, phase = 0;
             for (int32_t nt = 0; nt < n_tiles; ++nt) {
-                const uint32_t acc = (uint32_t)nt & 1u;
-                mbar_wait(acc_empty + acc, (((uint32_t)nt >> 1) & 1u) ^ 1u);
+                const uint32_t acc = (uint32_t)nt % TC_ACC;
+                mbar_wait(acc_empty + acc, (((uint32_t)nt / TC_ACC) & 1u) ^ 1u);
                 tc_fence_after();
                 const uint32_t tmem_d = tmem_base + acc * TC_BN;
                 for (int32_t kb = 0; kb < KB; ++kb) {
@@ -274,12 +282,65 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
         mask_refill();
         float thr = -INFINITY;  // score of the row's current k-th best (-inf while the buffer is not full)
         int count = 0, minpos = 0;
+        int nbuf = 0;  // survivors parked in this lane's buffer: (score bits << 32 | column), in item order
+        auto drain = [&]() {
+            int mx = (p.debug & 4) ? 0 : nbuf;
+#pragma unroll
+            for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+            for (int r = 0; r < mx; ++r) {
+                if (r >= nbuf) continue;
+                const unsigned long long ent = sbuf[r * TC_BM + row];
+                const float sc = __uint_as_float((uint32_t)(ent >> 32));
+                if (!(sc > thr)) continue;  // the threshold has risen since the survivor was parked
+                const uint32_t col = (uint32_t)(ent & 0xffffffffull);
+                // unsorted buffer of the k best: fill, then always replace the current minimum and rescan
+                // (k independent loads -- no dependent shifting chain)
+                const unsigned long long ck = ((unsigned long long)f2key_tc(sc) << 32) | (unsigned long long)(0xffffffffu - col);
+                const int slot = (count < k) ? count++ : minpos;
+                tk[slot * TC_BM + row] = ck;
+                if (count == k) {
+                    // minimum of the k entries: four independent running minima (the compare-select chain of a single one
+                    // is what an insertion costs), merged at the end; entries are unique, so the position follows the key
+                    unsigned long long m0 = ~0ull, m1 = ~0ull, m2 = ~0ull, m3 = ~0ull;
+                    int p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+                    int t = 0;
+                    for (; t + 4 <= k; t += 4) {
+                        const unsigned long long x0 = tk[(t + 0) * TC_BM + row], x1 = tk[(t + 1) * TC_BM + row];
+                        const unsigned long long x2 = tk[(t + 2) * TC_BM + row], x3 = tk[(t + 3) * TC_BM + row];
+                        if (x0 < m0) m0 = x0, p0 = t;
+                        if (x1 < m1) m1 = x1, p1 = t + 1;
+                        if (x2 < m2) m2 = x2, p2 = t + 2;
+                        if (x3 < m3) m3 = x3, p3 = t + 3;
+                    }
+                    for (; t < k; ++t) {
+                        const unsigned long long x0 = tk[t * TC_BM + row];
+                        if (x0 < m0) m0 = x0, p0 = t;
+                    }
+                    if (m1 < m0) m0 = m1, p0 = p1;
+                    if (m3 < m2) m2 = m3, p2 = p3;
+                    if (m2 < m0) m0 = m2, p0 = p2;
+                    minpos = p0;
+                    thr = key2f_tc((uint32_t)(m0 >> 32));
+                }
+            }
+            nbuf = 0;
+        };
         for (int32_t nt = 0; nt < n_tiles; ++nt) {
-            const uint32_t acc = (uint32_t)nt & 1u;
-            sbeta[acc * TC_BN + et] = p.beta[nt * TC_BN + et];  // padded columns carry -inf: never candidates
-            mbar_wait(acc_full + acc, ((uint32_t)nt >> 1) & 1u);
+            const uint32_t acc = (uint32_t)nt % TC_ACC;
+            const uint32_t bsl = (uint32_t)nt & 1u;  // beta tile slot
+            sbeta[bsl * TC_BN + et] = p.beta[nt * TC_BN + et];  // padded columns carry -inf: never candidates
+            mbar_wait(acc_full + acc, ((uint32_t)nt / TC_ACC) & 1u);
             tc_fence_after();
             asm volatile("bar.sync 1, 128;" ::: "memory");  // beta tile visible to the 4 epilogue warps
+            // The four epilogue warps move tile by tile together (the barrier above), so a drain by one of them stalls all:
+            // drains are therefore done by all four at the same tile boundary, requested through a flag by whichever warp
+            // sees a buffer filling up (flags rotate mod 3: set during tile nt, read at the start of tile nt + 1, cleared
+            // one tile later).
+            if (nt > 0) {
+                const bool want = s_req[(nt - 1) % 3] != 0u;
+                if (et == 0) s_req[(nt + 1) % 3] = 0u;
+                if (want) drain();
+            }
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_BN;
 #pragma unroll 1
             for (int ch = 0; ch < TC_BN / 32; ++ch) {
@@ -295,9 +356,9 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                     : "r"(taddr + (uint32_t)(ch * 32))
                     : "memory");
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-                if (!live || (p.debug & 1)) continue;
+                if (p.debug & 1) continue;  // (warp-uniform; rows beyond the chunk are masked below)
                 // pass 1 (branch-free): scores and the bitmask of those above the row's threshold
-                const float4 *bt = reinterpret_cast<const float4 *>(sbeta + acc * TC_BN + ch * 32);
+                const float4 *bt = reinterpret_cast<const float4 *>(sbeta + bsl * TC_BN + ch * 32);
                 uint32_t cand = 0u;
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -315,44 +376,37 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                     cand |= (s2 > thr ? 1u : 0u) << (4 * j4 + 2);
                     cand |= (s3 > thr ? 1u : 0u) << (4 * j4 + 3);
                 }
-                if (cand == 0u) continue;
-                // pass 2: the (few) survivors, in item order; their scores are parked in shared memory so that
-                // the loop over set bits can index them
+                if (!live) cand = 0u;
+                // known items of this chunk's column range are no candidates (the cursor only moves forward)
+                const int32_t col0 = nt * TC_BN + ch * 32;
+                while (mk0 < col0 + 32) {
+                    if (mk0 >= col0) cand &= ~(1u << (mk0 - col0));
+                    mk0 = mk1; mk1 = mk2; mk2 = mk3; mk3 = INT32_MAX;
+                    ++mcur;
+                    if (mk0 == INT32_MAX && mcur < me) mask_refill();
+                }
+                // pass 2, decoupled: a row gains a top-k entry only ~k ln(n/k) times over the whole pass, but SOME lane of the
+                // warp has a survivor in almost every chunk -- handled on the spot the warp would pay the replace-minimum scan
+                // in lockstep for every single one.  Survivors are therefore parked in the lane's own buffer (predicated
+                // stores, no divergence) and the buffers are drained together once some lane's is about to overflow: the
+                // warp then runs max-fill rounds instead of sum-of-fills.  (The threshold only rises at a drain; stale
+                // thresholds let a few more candidates through, they are re-checked when drained.)
 #pragma unroll
-                for (int j = 0; j < 32; ++j) sscr[j * TC_BM + row] = __uint_as_float(v[j]);
-                while (cand) {
-                    const int j = __ffs(cand) - 1;
-                    cand &= cand - 1u;
-                    const float sc = sscr[j * TC_BM + row];
-                    if (!(sc > thr)) continue;  // the threshold may have risen inside this chunk
-                    const int32_t col = nt * TC_BN + ch * 32 + j;
-                    while (mk0 < col) {  // skip known items that never were candidates
-                        mk0 = mk1; mk1 = mk2; mk2 = mk3; mk3 = INT32_MAX;
-                        ++mcur;
-                        if (mk0 == INT32_MAX && mcur < me) mask_refill();
-                    }
-                    if (mk0 == col) continue;  // known item
-                    // unsorted buffer of the k best: fill, then always replace the current minimum and rescan
-                    // (k independent loads -- no dependent shifting chain)
-                    const unsigned long long ck = ((unsigned long long)f2key_tc(sc) << 32) | (unsigned long long)(0xffffffffu - (uint32_t)col);
-                    const int slot = (count < k) ? count++ : minpos;
-                    tk[slot * TC_BM + row] = ck;
-                    if (count == k) {
-                        unsigned long long mn = ~0ull;
-                        int mp = 0;
-#pragma unroll 4
-                        for (int t = 0; t < k; ++t) {
-                            const unsigned long long x = tk[t * TC_BM + row];
-                            if (x < mn) {
-                                mn = x;
-                                mp = t;
-                            }
+                for (int half = 0; half < 2; ++half) {
+                    const uint32_t hc = (p.debug & 8) ? 0u : (cand >> (16 * half)) & 0xffffu;
+                    if (__ballot_sync(0xffffffffu, hc != 0u) == 0u) continue;  // (warp-uniform)
+                    if (__ballot_sync(0xffffffffu, nbuf > TC_CAP - 16) != 0u) drain();  // (rare: the shared drains come first)
+                    else if (__ballot_sync(0xffffffffu, nbuf > 6) != 0u && lane == 0) s_req[nt % 3] = 1u;
+#pragma unroll
+                    for (int j = 0; j < 16; ++j) {
+                        if ((hc >> j) & 1u) {
+                            sbuf[nbuf * TC_BM + row] = ((unsigned long long)v[16 * half + j] << 32) | (unsigned long long)(uint32_t)(col0 + 16 * half + j);
+                            ++nbuf;
                         }
-                        minpos = mp;
-                        thr = key2f_tc((uint32_t)(mn >> 32));
                     }
                 }
             }
+            if (nt + 1 == n_tiles) drain();
             tc_fence_before();
             mbar_arrive(acc_empty + acc);
         }
@@ -391,7 +445,7 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
     __syncthreads();
     if (warp == 1) {
         tc_fence_after();
-        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(256u) : "memory");
+        asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"((uint32_t)(TC_ACC * TC_BN)) : "memory");
     }
 }
 
@@ -465,7 +519,7 @@ int score_tc(int kernel, const int32_t *d_users, int64_t m, const float *d_P, co
     if (rc) return rc;
 
     const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_KCAP * TC_BM * 8 + 2 * TC_BN * 4 +
-                        32 * TC_BM * 4 + 128;
+                        (size_t)TC_CAP * TC_BM * 8 + 128;
     MFK_CUDA(cudaFuncSetAttribute(k_score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t u0 = 0; u0 < m; u0 += TC_USER_CHUNK) {
         const int64_t mt = (m - u0 < TC_USER_CHUNK) ? (m - u0) : TC_USER_CHUNK;
