@@ -31,6 +31,9 @@ constexpr int TC_TILE_BYTES = TC_BM * TC_BK * 4;        // 16 KB
 constexpr int TC_STAGE_BYTES = 4 * TC_TILE_BYTES;       // U_hi, U_lo, Q_hi, Q_lo
 constexpr int TC_THREADS = 192;
 constexpr int TC_ACC = 4;                               // TMEM accumulators (4 x 128 columns = all of tensor memory): the MMAs run up to three tiles ahead of the epilogue
+#ifndef MFK_TC_SOFT
+#define MFK_TC_SOFT 10  // parked survivors in some row from which a shared drain is requested for the next tile boundary
+#endif
 constexpr int TC_CAP = 32;                              // parked survivors per row before the warp drains its buffers
 constexpr int TC_USER_CHUNK = 128 * 256;                // users per workspace chunk
 
@@ -396,7 +399,7 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                     const uint32_t hc = (p.debug & 8) ? 0u : (cand >> (16 * half)) & 0xffffu;
                     if (__ballot_sync(0xffffffffu, hc != 0u) == 0u) continue;  // (warp-uniform)
                     if (__ballot_sync(0xffffffffu, nbuf > TC_CAP - 16) != 0u) drain();  // (rare: the shared drains come first)
-                    else if (__ballot_sync(0xffffffffu, nbuf > 6) != 0u && lane == 0) s_req[nt % 3] = 1u;
+                    else if (__ballot_sync(0xffffffffu, nbuf > MFK_TC_SOFT) != 0u && lane == 0) s_req[nt % 3] = 1u;
 #pragma unroll
                     for (int j = 0; j < 16; ++j) {
                         if ((hc >> j) & 1u) {
