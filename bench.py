@@ -41,7 +41,9 @@ WORKLOADS = {
 
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (bytes); None = not captured
-KNOWN_DRAM_TRAFFIC = {("ml-20m", "k_sgd_ring"): 322889984 + 611464448}  # profiles/r01b_ncu_full_k_sgd_ring_ml20m.txt
+# (profiles/r02_ncu_full_summary.txt: ML-20M shape, one launch each)
+KNOWN_DRAM_TRAFFIC = {("ml-20m", "k_sgd_batch (hot items)"): 219774208 + 525198592,
+                      ("ml-20m", "k_sgd_flat (the rest)"): 266747648 + 468194048}
 
 
 def load_peaks():
@@ -374,9 +376,10 @@ def run_ours_single(args):
                    "l2": f"per-epoch working set {(N * 16 + (U + I) * F * 4) / 1e6:.0f} MB vs 126 MB L2, no explicit flush",
                    "train_rmse_first_last": [rmse[0], rmse[-1]]},
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
-                     "traffic": KNOWN_DRAM_TRAFFIC.get((args.workload, "k_sgd_ring")),
-                     "traffic_note": "measured dram__bytes_read+write of the k_sgd_ring launch (ncu --set full, profiles/); "
-                                     "achieved/frac are algorithmic bytes / time and overstate HBM use (cache-resident rows)",
+                     "traffic": KNOWN_DRAM_TRAFFIC.get((args.workload, dominant)),
+                     "traffic_note": "measured dram__bytes_read+write of ONE launch of the dominant kernel (ncu --set full, "
+                                     "profiles/r02_ncu_full_summary.txt); achieved/frac are algorithmic bytes / time and overstate "
+                                     "HBM use (item rows live in shared memory, user rows mostly in L2)",
                      "kernel": "one epoch = " + " + ".join(ph["kernel"] for ph in phases),
                      "kernel_ms": sgd_ms, "dominant": dominant, "per_kernel": phases, "bytes_per_update": bytes_per_update,
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "ring_stats": ring_stats},
