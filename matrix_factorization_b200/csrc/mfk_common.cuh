@@ -41,6 +41,17 @@ struct DeviceProps {
 // cached per device; returns non-zero status on failure
 int device_props(DeviceProps *out);
 
+// Device memory of the plans and their scratch comes from a private, RETAINING memory pool: cudaMalloc / cudaFree of a
+// plan's gigabyte of buffers cost 40 ms .. 900 ms from call to call (map / unmap), which made every host-buffer fit
+// (mfk_*_host) vary by a second.  Same synchronisation semantics as cudaMalloc / cudaFree: pool_free waits for the
+// device before the block goes back to the pool.  MFK_POOL=0 falls back to cudaMalloc / cudaFree.
+cudaError_t pool_malloc(void **p, size_t bytes);
+template <typename T>
+static inline cudaError_t pool_malloc(T **p, size_t bytes) {
+    return pool_malloc(reinterpret_cast<void **>(p), bytes);
+}
+cudaError_t pool_free(void *p);
+
 // ---- device-side primitives ---------------------------------------------------------
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

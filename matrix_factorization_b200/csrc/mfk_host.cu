@@ -5,7 +5,9 @@
 //   mfk_bias_als_host <- baseline_model.py:283-362 (_als)
 // Each allocates device memory, copies in, runs n_epochs epochs (+ the per-epoch RMSE pass),
 // copies the parameters back and synchronises before returning.
+#include <chrono>
 #include <cmath>
+#include <cstdlib>
 #include <vector>
 
 #include "mfk_common.cuh"
@@ -17,16 +19,29 @@ struct DevBufs {
     cudaStream_t st = nullptr;
     ~DevBufs() {
         for (void *p : ptrs)
-            if (p) cudaFree(p);
+            if (p) pool_free(p);
         if (st) cudaStreamDestroy(st);
     }
     template <typename T>
     cudaError_t alloc(T **out, size_t count) {
         void *p = nullptr;
-        cudaError_t e = cudaMalloc(&p, (count ? count : 1) * sizeof(T));
+        cudaError_t e = pool_malloc(&p, (count ? count : 1) * sizeof(T));
         if (e == cudaSuccess) ptrs.push_back(p);
         *out = reinterpret_cast<T *>(p);
         return e;
+    }
+};
+
+// MFK_HOST_TIMING=1: wall-clock of the phases of a host call on stderr (diagnostics)
+struct PhaseTimer {
+    bool on = getenv("MFK_HOST_TIMING") != nullptr;
+    std::chrono::steady_clock::time_point t0 = std::chrono::steady_clock::now();
+    void lap(const char *what, cudaStream_t st) {
+        if (!on) return;
+        cudaStreamSynchronize(st);
+        auto t1 = std::chrono::steady_clock::now();
+        fprintf(stderr, "[mfk host] %-10s %8.1f ms\n", what, std::chrono::duration<double, std::milli>(t1 - t0).count());
+        t0 = t1;
     }
 };
 
@@ -72,6 +87,8 @@ extern "C" int mfk_kmf_sgd_host(int kernel, const int32_t *h_u, const int32_t *h
     MFK_CUDA(d.alloc(&dbi, (size_t)n_items));
     MFK_CUDA(d.alloc(&dsse, (size_t)(n_epochs > 0 ? n_epochs : 1)));
     MFK_CUDA(d.alloc((unsigned char **)&dws, mfk_sse_workspace_bytes()));
+    PhaseTimer tm;
+    tm.lap("alloc", d.st);
     if (n > 0) {
         MFK_CUDA(up(du, h_u, (size_t)n, d.st));
         MFK_CUDA(up(di, h_i, (size_t)n, d.st));
@@ -81,9 +98,11 @@ extern "C" int mfk_kmf_sgd_host(int kernel, const int32_t *h_u, const int32_t *h
     MFK_CUDA(up(dQ, h_Q, qn, d.st));
     MFK_CUDA(up(dbu, h_bu, (size_t)n_users, d.st));
     MFK_CUDA(up(dbi, h_bi, (size_t)n_items, d.st));
+    tm.lap("h2d", d.st);
     mfk_plan *plan = nullptr;
     int rc = mfk_plan_create(&plan, du, di, dr, n, n_users, n_items, opts, d.st);
     if (rc) return rc;
+    tm.lap("plan", d.st);
     if (h_order && n > 0) {
         rc = d.alloc(&dorder, (size_t)n) == cudaSuccess ? MFK_OK : MFK_ERR_CUDA;
         if (rc == MFK_OK) rc = mfk_plan_order(plan, dorder, d.st);
@@ -109,7 +128,9 @@ extern "C" int mfk_kmf_sgd_host(int kernel, const int32_t *h_u, const int32_t *h
             rc = MFK_ERR_CUDA;
         }
     }
+    tm.lap("epochs+d2h", d.st);
     mfk_plan_destroy(plan);
+    tm.lap("plan free", d.st);
     if (rc == MFK_OK)
         for (int e = 0; e < n_epochs; ++e) h_train_rmse[e] = n > 0 ? std::sqrt(h_train_rmse[e] / (double)n) : NAN;
     return rc;

@@ -18,8 +18,69 @@
 #include <cstring>
 #include <vector>
 
+#include <mutex>
+
 #include "mfk_common.cuh"
 #include "mfk_plan.h"
+
+// ---- retaining device-memory pool (see mfk_common.cuh)
+namespace mfk {
+namespace {
+struct PoolState {
+    bool tried = false, ok = false;
+    cudaMemPool_t pool = nullptr;
+    cudaStream_t stream = nullptr;
+};
+PoolState g_pools[64];
+std::mutex g_pool_mu;
+
+PoolState *pool_state() {
+    static const bool enabled = [] {
+        const char *e = getenv("MFK_POOL");
+        return !(e && atoi(e) == 0);
+    }();
+    if (!enabled) return nullptr;
+    int dev = 0;
+    if (cudaGetDevice(&dev) != cudaSuccess || dev < 0 || dev >= 64) return nullptr;
+    std::lock_guard<std::mutex> lk(g_pool_mu);
+    PoolState &st = g_pools[dev];
+    if (!st.tried) {
+        st.tried = true;
+        cudaMemPoolProps props = {};
+        props.allocType = cudaMemAllocationTypePinned;
+        props.handleTypes = cudaMemHandleTypeNone;
+        props.location.type = cudaMemLocationTypeDevice;
+        props.location.id = dev;
+        if (cudaMemPoolCreate(&st.pool, &props) == cudaSuccess &&
+            cudaStreamCreateWithFlags(&st.stream, cudaStreamNonBlocking) == cudaSuccess) {
+            unsigned long long keep = ~0ull;  // never give cached blocks back on a synchronisation
+            cudaMemPoolSetAttribute(st.pool, cudaMemPoolAttrReleaseThreshold, &keep);
+            st.ok = true;
+        } else {
+            cudaGetLastError();  // (clear; fall back to cudaMalloc)
+        }
+    }
+    return st.ok ? &st : nullptr;
+}
+}  // namespace
+
+cudaError_t pool_malloc(void **p, size_t bytes) {
+    PoolState *st = pool_state();
+    if (!st) return cudaMalloc(p, bytes);
+    cudaError_t e = cudaMallocFromPoolAsync(p, bytes, st->pool, st->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(st->stream);  // usable from any stream from here on
+    return e;
+}
+
+cudaError_t pool_free(void *p) {
+    if (!p) return cudaSuccess;
+    PoolState *st = pool_state();
+    if (!st) return cudaFree(p);
+    cudaError_t e = cudaDeviceSynchronize();  // what cudaFree does implicitly: nothing in flight may still use the block
+    cudaError_t e2 = cudaFreeAsync(p, st->stream);
+    return e != cudaSuccess ? e : e2;
+}
+}  // namespace mfk
 
 namespace mfk {
 
@@ -422,19 +483,19 @@ static int sort_by_degree(const int32_t *d_deg, int32_t n_ids, int32_t *d_sorted
     int32_t *keys_out = nullptr, *ids_in = nullptr;
     void *tmp = nullptr;
     size_t tmp_bytes = 0;
-    MFK_CUDA(cudaMalloc(&keys_out, sizeof(int32_t) * (size_t)n_ids));
-    MFK_CUDA(cudaMalloc(&ids_in, sizeof(int32_t) * (size_t)n_ids));
+    MFK_CUDA(pool_malloc(&keys_out, sizeof(int32_t) * (size_t)n_ids));
+    MFK_CUDA(pool_malloc(&ids_in, sizeof(int32_t) * (size_t)n_ids));
     k_iota<<<(n_ids + 255) / 256, 256, 0, st>>>(ids_in, n_ids);
     MFK_LAUNCH_CHECK();
     MFK_CUDA(cub::DeviceRadixSort::SortPairsDescending(nullptr, tmp_bytes, d_deg, keys_out, ids_in,
                                                        d_sorted_ids, n_ids, 0, 32, st));
-    MFK_CUDA(cudaMalloc(&tmp, tmp_bytes ? tmp_bytes : 1));
+    MFK_CUDA(pool_malloc(&tmp, tmp_bytes ? tmp_bytes : 1));
     MFK_CUDA(cub::DeviceRadixSort::SortPairsDescending(tmp, tmp_bytes, d_deg, keys_out, ids_in,
                                                        d_sorted_ids, n_ids, 0, 32, st));
     MFK_CUDA(cudaStreamSynchronize(st));
-    cudaFree(tmp);
-    cudaFree(keys_out);
-    cudaFree(ids_in);
+    pool_free(tmp);
+    pool_free(keys_out);
+    pool_free(ids_in);
     return MFK_OK;
 }
 
