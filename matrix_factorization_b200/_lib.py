@@ -10,7 +10,8 @@ import ctypes as C
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libmfk_b200.so")
+# (MFK_LIB_PATH: another build of the same library, for A/B experiments of kernel variants)
+LIB_PATH = os.environ.get("MFK_LIB_PATH") or os.path.join(_HERE, "csrc", "libmfk_b200.so")
 
 KERNEL_IDS = {"linear": 0, "sigmoid": 1, "rbf": 2}
 ERR_NAMES = {1: "MFK_ERR_ARG", 2: "MFK_ERR_CUDA", 3: "MFK_ERR_UNSUPPORTED", 4: "MFK_ERR_NO_DEVICE"}

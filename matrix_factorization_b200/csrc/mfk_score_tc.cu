@@ -11,12 +11,14 @@
 //   warp 1      TMEM allocator + MMA issuer: per k-block 4 x 3 tcgen05.mma.kind::tf32 (M=128, N=128, K=8) into one of
 //               four TMEM accumulators (all 512 columns), tcgen05.commit releases the stage / publishes the accumulator;
 //   warps 2..5  epilogue: tcgen05.ld of the thread's row (one user per thread), key = alpha*acc + beta[item],
-//               known-item mask by a cursor over the user's sorted list, threshold test against the row's current
-//               k-th best; the survivors are PARKED in the row's small buffer and the four warps drain their buffers
-//               together at a tile boundary (replace-minimum into the row's unsorted top-k list in shared memory) --
-//               a row gains an entry only ~k ln(n/k) times per pass, but some row of a warp does in almost every chunk,
-//               so inserting on the spot would make the whole warp (and, through the per-tile barrier, all four) pay
-//               the scan for each one.
+//               known-item mask by a cursor over the user's sorted list (ids prefetched one block of four ahead),
+//               threshold test against the row's current k-th best; the survivors are PARKED in the row's small buffer
+//               and a warp drains its buffers at a tile boundary (replace-minimum into the row's unsorted top-k list in
+//               shared memory) -- a row gains an entry only ~k ln(n/k) times per pass, but some row of a warp does in
+//               almost every chunk, so inserting on the spot would make the whole warp pay the scan for each one.
+//               The four warps are independent of each other (each keeps its own copy of the tile's beta values and
+//               there is no barrier among them): they only meet in the 128 arrivals that free an accumulator, and the
+//               MMAs run up to three tiles ahead, so a warp that drains does not hold up the others.
 #include <cuda.h>
 
 #include <cstdint>
@@ -34,8 +36,8 @@ constexpr int TC_ACC = 4;                               // TMEM accumulators (4 
 #ifndef MFK_TC_SOFT
 #define MFK_TC_SOFT 10  // parked survivors in some row from which a shared drain is requested for the next tile boundary
 #endif
-constexpr int TC_CAP = 32;                              // parked survivors per row before the warp drains its buffers
-constexpr int TC_USER_CHUNK = 128 * 256;                // users per workspace chunk
+constexpr int TC_CAP = 30;                              // parked survivors per row (a half chunk can add 16: a warp drains beyond TC_CAP - 16)
+constexpr int TC_USER_CHUNK = 128 * 148 * 64;           // users per launch (whole waves of 148 CTAs; one launch for every shape the workspace is sized for)
 
 struct TcParams {
     int32_t m;        // users in this chunk
@@ -172,12 +174,11 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
     unsigned char *stage_mem = base;
     // per-row top-k buffer: composite (sortable score key << 32 | ~item) -- larger = better, unique
     unsigned long long *tk = reinterpret_cast<unsigned long long *>(base + TC_STAGES * TC_STAGE_BYTES);  // [KCAP][128]
-    float *sbeta = reinterpret_cast<float *>(tk + TC_KCAP * TC_BM);                                       // [2][128]
-    unsigned long long *sbuf = reinterpret_cast<unsigned long long *>(sbeta + 2 * TC_BN);  // [TC_CAP][128] parked survivors per row
+    float *sbeta = reinterpret_cast<float *>(tk + TC_KCAP * TC_BM);                                       // [4 epilogue warps][128]
+    unsigned long long *sbuf = reinterpret_cast<unsigned long long *>(sbeta + 4 * TC_BN);  // [TC_CAP][128] parked survivors per row
     uint64_t *bars = reinterpret_cast<uint64_t *>(sbuf + TC_CAP * TC_BM);
     uint64_t *full = bars, *empty = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + TC_ACC;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + TC_ACC);
-    volatile uint32_t *s_req = tmem_slot + 1;  // [3] "some epilogue warp wants a drain", one flag per tile (mod 3)
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int32_t m0 = blockIdx.x * TC_BM;
@@ -201,7 +202,6 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     for (int j = threadIdx.x; j < TC_KCAP * TC_BM; j += TC_THREADS) tk[j] = 0ull;
-    if (threadIdx.x < 3) s_req[threadIdx.x] = 0u;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -266,7 +266,6 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
         // ===== epilogue: thread <-> TMEM lane <-> user row =====
         const int quad = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) ..
         const int row = quad * 32 + lane;
-        const int et = (warp - 2) * 32 + lane;  // 0..127 index among the epilogue threads
         const bool live = (m0 + row) < p.m;
         const int32_t k = p.k;
         // known-item mask: the row's sorted list is consumed in item order; the next four ids sit in registers
@@ -275,13 +274,20 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
             mcur = p.mask_ptr[m0 + row];
             me = p.mask_ptr[m0 + row + 1];
         }
+        // (mk: the block in use;  nk: the block after it, requested when mk was taken over -- its load latency is off the path)
         int32_t mk0 = INT32_MAX, mk1 = INT32_MAX, mk2 = INT32_MAX, mk3 = INT32_MAX;
-        auto mask_refill = [&]() {
-            mk0 = (mcur + 0 < me) ? p.mask_items[mcur + 0] : INT32_MAX;
-            mk1 = (mcur + 1 < me) ? p.mask_items[mcur + 1] : INT32_MAX;
-            mk2 = (mcur + 2 < me) ? p.mask_items[mcur + 2] : INT32_MAX;
-            mk3 = (mcur + 3 < me) ? p.mask_items[mcur + 3] : INT32_MAX;
+        int32_t nk0 = INT32_MAX, nk1 = INT32_MAX, nk2 = INT32_MAX, nk3 = INT32_MAX;
+        auto mask_load_next = [&](int64_t at) {
+            nk0 = (at + 0 < me) ? __ldg(p.mask_items + at + 0) : INT32_MAX;
+            nk1 = (at + 1 < me) ? __ldg(p.mask_items + at + 1) : INT32_MAX;
+            nk2 = (at + 2 < me) ? __ldg(p.mask_items + at + 2) : INT32_MAX;
+            nk3 = (at + 3 < me) ? __ldg(p.mask_items + at + 3) : INT32_MAX;
         };
+        auto mask_refill = [&]() {  // mcur: list position of the first id of the block that becomes current
+            mk0 = nk0, mk1 = nk1, mk2 = nk2, mk3 = nk3;
+            mask_load_next(mcur + 4);
+        };
+        mask_load_next(mcur);
         mask_refill();
         float thr = -INFINITY;  // score of the row's current k-th best (-inf while the buffer is not full)
         int count = 0, minpos = 0;
@@ -328,22 +334,20 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
             }
             nbuf = 0;
         };
+        // the warp's own copy of the tile's 128 beta values (a lane brings four of them; the next tile's are requested a
+        // tile ahead); padded columns carry -inf: never candidates
+        float *wbeta = sbeta + (warp - 2) * TC_BN;
+        float4 bnext = *reinterpret_cast<const float4 *>(p.beta + 4 * lane);
         for (int32_t nt = 0; nt < n_tiles; ++nt) {
             const uint32_t acc = (uint32_t)nt % TC_ACC;
-            const uint32_t bsl = (uint32_t)nt & 1u;  // beta tile slot
-            sbeta[bsl * TC_BN + et] = p.beta[nt * TC_BN + et];  // padded columns carry -inf: never candidates
+            __syncwarp();  // (every lane is done with the previous tile's values)
+            *reinterpret_cast<float4 *>(wbeta + 4 * lane) = bnext;
+            if (nt + 1 < n_tiles) bnext = *reinterpret_cast<const float4 *>(p.beta + (size_t)(nt + 1) * TC_BN + 4 * lane);
+            __syncwarp();
+            // a tile boundary is where a warp drains (one round per parked survivor of its fullest row)
+            if (__ballot_sync(0xffffffffu, nbuf > MFK_TC_SOFT) != 0u) drain();
             mbar_wait(acc_full + acc, ((uint32_t)nt / TC_ACC) & 1u);
             tc_fence_after();
-            asm volatile("bar.sync 1, 128;" ::: "memory");  // beta tile visible to the 4 epilogue warps
-            // The four epilogue warps move tile by tile together (the barrier above), so a drain by one of them stalls all:
-            // drains are therefore done by all four at the same tile boundary, requested through a flag by whichever warp
-            // sees a buffer filling up (flags rotate mod 3: set during tile nt, read at the start of tile nt + 1, cleared
-            // one tile later).
-            if (nt > 0) {
-                const bool want = s_req[(nt - 1) % 3] != 0u;
-                if (et == 0) s_req[(nt + 1) % 3] = 0u;
-                if (want) drain();
-            }
             const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_BN;
 #pragma unroll 1
             for (int ch = 0; ch < TC_BN / 32; ++ch) {
@@ -361,7 +365,7 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                 asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
                 if (p.debug & 1) continue;  // (warp-uniform; rows beyond the chunk are masked below)
                 // pass 1 (branch-free): scores and the bitmask of those above the row's threshold
-                const float4 *bt = reinterpret_cast<const float4 *>(sbeta + bsl * TC_BN + ch * 32);
+                const float4 *bt = reinterpret_cast<const float4 *>(wbeta + ch * 32);
                 uint32_t cand = 0u;
 #pragma unroll
                 for (int j4 = 0; j4 < 8; ++j4) {
@@ -398,15 +402,22 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                 for (int half = 0; half < 2; ++half) {
                     const uint32_t hc = (p.debug & 8) ? 0u : (cand >> (16 * half)) & 0xffffu;
                     if (__ballot_sync(0xffffffffu, hc != 0u) == 0u) continue;  // (warp-uniform)
-                    if (__ballot_sync(0xffffffffu, nbuf > TC_CAP - 16) != 0u) drain();  // (rare: the shared drains come first)
-                    else if (__ballot_sync(0xffffffffu, nbuf > MFK_TC_SOFT) != 0u && lane == 0) s_req[nt % 3] = 1u;
+                    if (__ballot_sync(0xffffffffu, nbuf > TC_CAP - 16) != 0u) drain();  // (rare: the drains at tile boundaries come first)
+                    // slot of survivor j = nbuf + survivors before it: no dependent chain through the counter; groups of four
+                    // columns without a survivor in any lane are skipped
+                    const uint32_t wany = __reduce_or_sync(0xffffffffu, hc);
 #pragma unroll
-                    for (int j = 0; j < 16; ++j) {
-                        if ((hc >> j) & 1u) {
-                            sbuf[nbuf * TC_BM + row] = ((unsigned long long)v[16 * half + j] << 32) | (unsigned long long)(uint32_t)(col0 + 16 * half + j);
-                            ++nbuf;
+                    for (int g = 0; g < 4; ++g) {
+                        if (((wany >> (4 * g)) & 0xfu) == 0u) continue;  // (warp-uniform)
+#pragma unroll
+                        for (int j = 4 * g; j < 4 * g + 4; ++j) {
+                            if ((hc >> j) & 1u) {
+                                const int slot = nbuf + __popc(hc & ((1u << j) - 1u));
+                                sbuf[slot * TC_BM + row] = ((unsigned long long)v[16 * half + j] << 32) | (unsigned long long)(uint32_t)(col0 + 16 * half + j);
+                            }
                         }
                     }
+                    nbuf += __popc(hc);
                 }
             }
             if (nt + 1 == n_tiles) drain();
@@ -521,7 +532,7 @@ int score_tc(int kernel, const int32_t *d_users, int64_t m, const float *d_P, co
     if (rc == MFK_OK) rc = make_tmap(&tm_qlo, qlo, np, kp);
     if (rc) return rc;
 
-    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_KCAP * TC_BM * 8 + 2 * TC_BN * 4 +
+    const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_KCAP * TC_BM * 8 + 4 * TC_BN * 4 +
                         (size_t)TC_CAP * TC_BM * 8 + 128;
     MFK_CUDA(cudaFuncSetAttribute(k_score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     for (int64_t u0 = 0; u0 < m; u0 += TC_USER_CHUNK) {

@@ -1,6 +1,12 @@
 #!/bin/bash
-# A/B of compile-time variants on the isolated chain and on phase 1:  tools/gpu_ab.sh "DEF1" "DEF2" ...
-for defs in "$@"; do
-  MFK_NVCC_DEFS="$defs" python -m matrix_factorization_b200.build --force > /dev/null 2>&1
-  echo "== $defs: $(python tools/prof_chain.py 2>&1 | tail -1 | cut -c1-70) | phase1 $(python tools/prof_hot.py --phases 1 --epochs 3 2>&1 | grep 'epoch ms' | tail -1 | cut -c1-28)"
+# A/B of library variants (tools/build_variant.sh) on the isolated chain and the hot-item phase
+out=gpurun_out/ab.log
+: > $out
+V=matrix_factorization_b200/csrc/variants
+for v in "" $@; do
+  if [ -z "$v" ]; then unset MFK_LIB_PATH; name=default; else export MFK_LIB_PATH=$PWD/$V/libmfk_$v.so; name=$v; fi
+  a=$(timeout 120 python tools/prof_chain.py --epochs 3 2>&1 | tail -1 | awk '{print $NF}')
+  b=$(timeout 120 python tools/prof_chain.py --factors 256 --users 200000 --epochs 3 2>&1 | tail -1 | awk '{print $NF}')
+  c=$(timeout 200 python tools/prof_hot.py --phases 1 --epochs 3 2>&1 | grep "epoch ms" | tail -1 | cut -c1-26)
+  echo "$name chain128 $a chain256 $b phase1 $c" | tee -a $out
 done
