@@ -13,12 +13,23 @@
 //   warps 2..5  epilogue: tcgen05.ld of the thread's row (one user per thread), key = alpha*acc + beta[item],
 //               known-item mask by a cursor over the user's sorted list (ids prefetched one block of four ahead),
 //               threshold test against the row's current k-th best; the survivors are PARKED in the row's small buffer
-//               and a warp drains its buffers at a tile boundary (replace-minimum into the row's unsorted top-k list in
+//               and a warp drains its buffers at a tile boundary (replace-root + sift-down in the row's k-entry min-heap in
 //               shared memory) -- a row gains an entry only ~k ln(n/k) times per pass, but some row of a warp does in
 //               almost every chunk, so inserting on the spot would make the whole warp pay the scan for each one.
 //               The four warps are independent of each other (each keeps its own copy of the tile's beta values and
 //               there is no barrier among them): they only meet in the 128 arrivals that free an accumulator, and the
 //               MMAs run up to three tiles ahead, so a warp that drains does not hold up the others.
+//
+// Rows of up to 128 floats (TS = true): the user tile is the A operand IN TENSOR MEMORY for the whole life of the CTA --
+// the epilogue threads split their own row of P into hi / lo and write it with tcgen05.st (columns 0..127 hi, 128..255
+// lo; two accumulators in the other 256 columns), the MMAs are  tcgen05.mma [d], [a_tmem], b_desc .  Only the item
+// tiles stream through shared memory (four stages of {Q_hi, Q_lo}): half the L2 -> SM traffic (the 128 KB user tile was
+// re-read for every item tile) and half the operand reads of the tensor core from shared memory, which it shares with
+// the epilogue's top-k lists.  With the shared memory that frees (ES = 2, k <= 55) EIGHT epilogue warps work on a tile: two
+// threads per user row, each with the columns of one half of the tile, its own top-k list and its own cursor over the
+// known-item list; they exchange only their thresholds (the k-th best of either half is a lower bound of the row's k-th
+// best) and merge their two sorted lists at the end.  The epilogue is latency-bound with one warp per scheduler; two
+// per scheduler overlap.
 #include <cuda.h>
 
 #include <cstdint>
@@ -53,6 +64,8 @@ struct TcParams {
     const int64_t *mask_ptr;     // [m + 1] (already offset to this chunk) or null
     const int32_t *mask_items;   // sorted ascending inside every row
     float mu, gamma, a, c, lo, hi;
+    const float *P;              // TS: user factors [n_users][ldP] (the epilogue threads read their rows themselves)
+    int32_t ldP, F;
     int32_t bound;
     int32_t debug;               // MFK_TC_DEBUG bits: 1 = skip epilogue scan, 2 = skip MMA issue (timing experiments only)
     float *out_scores;           // [m][k]
@@ -71,7 +84,10 @@ __device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes) {
 __device__ __forceinline__ void mbar_arrive(uint64_t *bar) {
     asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
 }
-// bounded wait: a pipeline bug must trap, not hang the GPU
+// bounded wait: a pipeline bug must trap, not hang the GPU.  The suspend-time hint parks the thread in the barrier unit until
+// the phase completes (or the hint runs out): without it try_wait comes back at once and the loop spins -- ncu counted 1.2 G of
+// the kernel's 4.2 G warp instructions in this loop, issue slots taken from the epilogue warps of the same scheduler.
+constexpr uint32_t kMbarSuspendNs = 20000;
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
     const uint32_t addr = smem_u32(bar);
     unsigned long long t0 = 0;
@@ -79,10 +95,10 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity) {
         uint32_t ok;
         asm volatile(
             "{\n\t.reg .pred p;\n\t"
-            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2, %3;\n\t"
             "selp.b32 %0, 1, 0, p;\n\t}"
             : "=r"(ok)
-            : "r"(addr), "r"(parity)
+            : "r"(addr), "r"(parity), "r"(kMbarSuspendNs)
             : "memory");
         if (ok) return;
         if ((it & 0xfff) == 0xfff) {
@@ -113,6 +129,27 @@ __device__ __forceinline__ void umma_tf32(uint32_t tmem_d, uint64_t adesc, uint6
         "setp.ne.b32 p, %4, 0;\n\t"
         "tcgen05.mma.cta_group::1.kind::tf32 [%0], %1, %2, %3, p;\n\t}"
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+// A operand in tensor memory (lane = row, one 32-bit column per k), B from shared memory
+__device__ __forceinline__ void umma_tf32_ts(uint32_t tmem_d, uint32_t tmem_a, uint64_t bdesc, uint32_t idesc,
+                                             uint32_t accumulate) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::tf32 [%0], [%1], %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "r"(tmem_a), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_st32(uint32_t taddr, const uint32_t (&r)[32]) {
+    asm volatile(
+        "tcgen05.st.sync.aligned.32x32b.x32.b32 [%0], "
+        "{%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
+        "%28,%29,%30,%31,%32};"
+        ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]), "r"(r[8]),
+          "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]), "r"(r[16]), "r"(r[17]),
+          "r"(r[18]), "r"(r[19]), "r"(r[20]), "r"(r[21]), "r"(r[22]), "r"(r[23]), "r"(r[24]), "r"(r[25]), "r"(r[26]),
+          "r"(r[27]), "r"(r[28]), "r"(r[29]), "r"(r[30]), "r"(r[31])
         : "memory");
 }
 // K-major operand tile, 128-byte swizzle, 8-row groups 1024 bytes apart (what the TMA box {32 floats, rows} writes)
@@ -164,7 +201,8 @@ __global__ void k_make_beta(const float *__restrict__ bi, const float *__restric
 }
 
 // ---------------------------------------------------------------- main kernel
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <bool TS, int ES>
+__global__ void __launch_bounds__(64 + 128 * ES, 1)
 k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ CUtensorMap tm_ulo,
            const __grid_constant__ CUtensorMap tm_qhi, const __grid_constant__ CUtensorMap tm_qlo, TcParams p) {
     extern __shared__ unsigned char smem_dyn[];
@@ -173,12 +211,24 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
     unsigned char *base = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
     unsigned char *stage_mem = base;
     // per-row top-k buffer: composite (sortable score key << 32 | ~item) -- larger = better, unique
-    unsigned long long *tk = reinterpret_cast<unsigned long long *>(base + TC_STAGES * TC_STAGE_BYTES);  // [KCAP][128]
-    float *sbeta = reinterpret_cast<float *>(tk + TC_KCAP * TC_BM);                                       // [4 epilogue warps][128]
-    unsigned long long *sbuf = reinterpret_cast<unsigned long long *>(sbeta + 4 * TC_BN);  // [TC_CAP][128] parked survivors per row
-    uint64_t *bars = reinterpret_cast<uint64_t *>(sbuf + TC_CAP * TC_BM);
-    uint64_t *full = bars, *empty = bars + TC_STAGES, *acc_full = bars + 2 * TC_STAGES, *acc_empty = acc_full + TC_ACC;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + TC_ACC);
+    static_assert(ES == 1 || (ES == 2 && TS), "two epilogue sets need the shared memory the TS variant frees");
+    // TS: stages of {Q_hi, Q_lo} (half the bytes; four of them, or two next to the second set's lists), two accumulators
+    // behind the 256 columns of the A operand
+    constexpr int NST = TS ? (ES == 2 ? 2 : 4) : TC_STAGES, STB = TS ? TC_STAGE_BYTES / 2 : TC_STAGE_BYTES;
+    constexpr int NTHR = 64 + 128 * ES;
+    constexpr int CAPV = ES == 2 ? 24 : TC_CAP;            // parked survivors per row and set
+    constexpr int SOFTV = ES == 2 ? 5 : MFK_TC_SOFT;
+    const int KR = ES == 2 ? p.k : TC_KCAP;                // rows of a top-k list
+    unsigned long long *tk = reinterpret_cast<unsigned long long *>(base + NST * STB);  // [ES][KR][128]
+    float *sbeta = reinterpret_cast<float *>(tk + ES * KR * TC_BM);                      // [4 ES epilogue warps][128]
+    unsigned long long *sbuf = reinterpret_cast<unsigned long long *>(sbeta + 4 * ES * TC_BN);  // [ES][CAPV][128] parked survivors per row
+    volatile float *s_thr = reinterpret_cast<volatile float *>(sbuf + ES * CAPV * TC_BM);       // [2][128] k-th best of either half (ES = 2)
+    volatile int32_t *s_cnt = reinterpret_cast<volatile int32_t *>(s_thr + 2 * TC_BM);          // [128] entries of the second set's list
+    uint64_t *bars = reinterpret_cast<uint64_t *>(const_cast<int32_t *>(s_cnt) + TC_BM);
+    constexpr int NACC = TS ? 2 : TC_ACC;
+    constexpr uint32_t ACC_COL0 = TS ? 2 * TC_BN : 0;
+    uint64_t *full = bars, *empty = bars + NST, *acc_full = bars + 2 * NST, *acc_empty = acc_full + NACC;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(acc_empty + NACC);
 
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
     const int32_t m0 = blockIdx.x * TC_BM;
@@ -186,13 +236,13 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
     const int32_t KB = p.kblocks;
 
     if (threadIdx.x == 0) {
-        for (int s = 0; s < TC_STAGES; ++s) {
+        for (int s = 0; s < NST; ++s) {
             mbar_init(full + s, 1);
             mbar_init(empty + s, 1);
         }
-        for (int a = 0; a < TC_ACC; ++a) {
+        for (int a = 0; a < NACC; ++a) {
             mbar_init(acc_full + a, 1);
-            mbar_init(acc_empty + a, 128);
+            mbar_init(acc_empty + a, 128 * ES);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -201,7 +251,8 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                      : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
-    for (int j = threadIdx.x; j < TC_KCAP * TC_BM; j += TC_THREADS) tk[j] = 0ull;
+    for (int j = threadIdx.x; j < ES * KR * TC_BM; j += NTHR) tk[j] = 0ull;
+    for (int j = threadIdx.x; j < 2 * TC_BM; j += NTHR) s_thr[j] = -INFINITY;
     tc_fence_before();
     __syncthreads();
     tc_fence_after();
@@ -214,13 +265,18 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
             for (int32_t nt = 0; nt < n_tiles; ++nt) {
                 for (int32_t kb = 0; kb < KB; ++kb) {
                     mbar_wait(empty + stage, phase ^ 1u);
-                    unsigned char *st = stage_mem + stage * TC_STAGE_BYTES;
-                    mbar_expect_tx(full + stage, TC_STAGE_BYTES);
-                    tma_load_2d(st, &tm_uhi, kb * TC_BK, m0, full + stage);
-                    tma_load_2d(st + TC_TILE_BYTES, &tm_ulo, kb * TC_BK, m0, full + stage);
-                    tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_qhi, kb * TC_BK, nt * TC_BN, full + stage);
-                    tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_qlo, kb * TC_BK, nt * TC_BN, full + stage);
-                    if (++stage == TC_STAGES) {
+                    unsigned char *st = stage_mem + stage * STB;
+                    mbar_expect_tx(full + stage, STB);
+                    if (TS) {
+                        tma_load_2d(st, &tm_qhi, kb * TC_BK, nt * TC_BN, full + stage);
+                        tma_load_2d(st + TC_TILE_BYTES, &tm_qlo, kb * TC_BK, nt * TC_BN, full + stage);
+                    } else {
+                        tma_load_2d(st, &tm_uhi, kb * TC_BK, m0, full + stage);
+                        tma_load_2d(st + TC_TILE_BYTES, &tm_ulo, kb * TC_BK, m0, full + stage);
+                        tma_load_2d(st + 2 * TC_TILE_BYTES, &tm_qhi, kb * TC_BK, nt * TC_BN, full + stage);
+                        tma_load_2d(st + 3 * TC_TILE_BYTES, &tm_qlo, kb * TC_BK, nt * TC_BN, full + stage);
+                    }
+                    if (++stage == NST) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -229,32 +285,43 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
         }
     } else if (warp == 1) {
         // ===== MMA issuer (one elected lane) =====
+        if (TS) {  // the epilogue threads have written the user tile into tensor memory
+            asm volatile("bar.sync 2, %0;" ::"n"(128 * ES + 32) : "memory");
+            tc_fence_after();
+        }
         if (lane == 0) {
             // instruction descriptor: D = F32, A = B = TF32, both K-major, N = 128, M = 128
             const uint32_t idesc = (1u << 4) | (2u << 7) | (2u << 10) | ((uint32_t)(TC_BN >> 3) << 17) |
                                    ((uint32_t)(TC_BM >> 4) << 24);
             uint32_t stage = 0, phase = 0;
             for (int32_t nt = 0; nt < n_tiles; ++nt) {
-                const uint32_t acc = (uint32_t)nt % TC_ACC;
-                mbar_wait(acc_empty + acc, (((uint32_t)nt / TC_ACC) & 1u) ^ 1u);
+                const uint32_t acc = (uint32_t)nt % NACC;
+                mbar_wait(acc_empty + acc, (((uint32_t)nt / NACC) & 1u) ^ 1u);
                 tc_fence_after();
-                const uint32_t tmem_d = tmem_base + acc * TC_BN;
+                const uint32_t tmem_d = tmem_base + ACC_COL0 + acc * TC_BN;
                 for (int32_t kb = 0; kb < KB; ++kb) {
                     mbar_wait(full + stage, phase);
                     tc_fence_after();
-                    const uint32_t sa = smem_u32(stage_mem + stage * TC_STAGE_BYTES);
+                    const uint32_t sa = smem_u32(stage_mem + stage * STB);
                     const uint64_t d_uhi = umma_desc_sw128(sa), d_ulo = umma_desc_sw128(sa + TC_TILE_BYTES);
-                    const uint64_t d_qhi = umma_desc_sw128(sa + 2 * TC_TILE_BYTES), d_qlo = umma_desc_sw128(sa + 3 * TC_TILE_BYTES);
+                    const uint64_t d_qhi = umma_desc_sw128(sa + (TS ? 0 : 2) * TC_TILE_BYTES), d_qlo = umma_desc_sw128(sa + (TS ? 1 : 3) * TC_TILE_BYTES);
 #pragma unroll
                     for (int k4 = 0; k4 < TC_BK / 8; ++k4) {
                         const uint64_t adv = (uint64_t)((k4 * 32) >> 4);  // 8 tf32 = 32 bytes inside the swizzle atom
                         if (p.debug & 2) continue;
-                        umma_tf32(tmem_d, d_uhi + adv, d_qhi + adv, idesc, (kb | k4) ? 1u : 0u);
-                        umma_tf32(tmem_d, d_uhi + adv, d_qlo + adv, idesc, 1u);
-                        umma_tf32(tmem_d, d_ulo + adv, d_qhi + adv, idesc, 1u);
+                        if (TS) {
+                            const uint32_t a_hi = tmem_base + (uint32_t)(kb * TC_BK + k4 * 8), a_lo = a_hi + TC_BN;
+                            umma_tf32_ts(tmem_d, a_hi, d_qhi + adv, idesc, (kb | k4) ? 1u : 0u);
+                            umma_tf32_ts(tmem_d, a_hi, d_qlo + adv, idesc, 1u);
+                            umma_tf32_ts(tmem_d, a_lo, d_qhi + adv, idesc, 1u);
+                        } else {
+                            umma_tf32(tmem_d, d_uhi + adv, d_qhi + adv, idesc, (kb | k4) ? 1u : 0u);
+                            umma_tf32(tmem_d, d_uhi + adv, d_qlo + adv, idesc, 1u);
+                            umma_tf32(tmem_d, d_ulo + adv, d_qhi + adv, idesc, 1u);
+                        }
                     }
                     umma_commit(empty + stage);  // stage reusable once these MMAs have read it
-                    if (++stage == TC_STAGES) {
+                    if (++stage == NST) {
                         stage = 0;
                         phase ^= 1u;
                     }
@@ -266,8 +333,43 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
         // ===== epilogue: thread <-> TMEM lane <-> user row =====
         const int quad = warp & 3;  // a warp may only touch TMEM lanes 32*(warp%4) ..
         const int row = quad * 32 + lane;
+        const int set = (warp - 2) >> 2;  // ES = 2: the half of every tile this thread scans
+        unsigned long long *const tks = tk + set * KR * TC_BM;
+        unsigned long long *const sbufs = sbuf + set * CAPV * TC_BM;
         const bool live = (m0 + row) < p.m;
         const int32_t k = p.k;
+        float un_row = 0.f;  // TS: |p|^2 of the row (rbf)
+        if (TS && set == 0) {
+            // the thread's own user row, split into the tf32 part and the fp32 remainder, into tensor memory:
+            // lane `row`, columns c (hi) and 128 + c (lo)
+            const float *prow = p.P + (size_t)(live ? p.users[m0 + row] : 0) * p.ldP;
+            const uint32_t trow = tmem_base + ((uint32_t)(quad * 32) << 16);
+            for (int c0 = 0; c0 < p.kblocks * TC_BK; c0 += 32) {
+                uint32_t hi[32], lo[32];
+#pragma unroll
+                for (int c4 = 0; c4 < 8; ++c4) {
+                    const int c = c0 + 4 * c4;
+                    float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
+                    if (live && c < p.F) x = __ldg(reinterpret_cast<const float4 *>(prow + c));  // (padding columns of a row are zero)
+                    const float xs[4] = {x.x, x.y, x.z, x.w};
+#pragma unroll
+                    for (int e = 0; e < 4; ++e) {
+                        uint32_t hb;
+                        asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(hb) : "f"(xs[e]));
+                        hi[4 * c4 + e] = hb;
+                        lo[4 * c4 + e] = __float_as_uint(xs[e] - __uint_as_float(hb));
+                        un_row = fmaf(xs[e], xs[e], un_row);
+                    }
+                }
+                tmem_st32(trow + (uint32_t)c0, hi);
+                tmem_st32(trow + (uint32_t)(TC_BN + c0), lo);
+            }
+            asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");
+        }
+        if (TS) {
+            tc_fence_before();
+            asm volatile("bar.sync 2, %0;" ::"n"(128 * ES + 32) : "memory");  // -> the MMA issuer
+        }
         // known-item mask: the row's sorted list is consumed in item order; the next four ids sit in registers
         int64_t mcur = 0, me = 0;
         if (live && p.mask_ptr) {
@@ -289,8 +391,9 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
         };
         mask_load_next(mcur);
         mask_refill();
-        float thr = -INFINITY;  // score of the row's current k-th best (-inf while the buffer is not full)
-        int count = 0, minpos = 0;
+        float thr = -INFINITY;  // candidates must beat it: the k-th best of this thread's list (-inf while the list is not full)
+        float pthr = -INFINITY;  // ... or of the other half's (ES = 2)
+        int count = 0;
         int nbuf = 0;  // survivors parked in this lane's buffer: (score bits << 32 | column), in item order
         auto drain = [&]() {
             int mx = (p.debug & 4) ? 0 : nbuf;
@@ -298,38 +401,43 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
             for (int o = 16; o > 0; o >>= 1) mx = max(mx, __shfl_xor_sync(0xffffffffu, mx, o));
             for (int r = 0; r < mx; ++r) {
                 if (r >= nbuf) continue;
-                const unsigned long long ent = sbuf[r * TC_BM + row];
+                const unsigned long long ent = sbufs[r * TC_BM + row];
                 const float sc = __uint_as_float((uint32_t)(ent >> 32));
                 if (!(sc > thr)) continue;  // the threshold has risen since the survivor was parked
                 const uint32_t col = (uint32_t)(ent & 0xffffffffull);
-                // unsorted buffer of the k best: fill, then always replace the current minimum and rescan
-                // (k independent loads -- no dependent shifting chain)
+                // the row's k best as a binary MIN-HEAP in shared memory (entry i of the row at tks[i * 128 + row]): the list fills
+                // in arrival order and is heapified once when it is full; from then on a survivor replaces the root and sifts
+                // down -- at most log2(k) dependent steps of two loads and a 64-bit compare, instead of a scan of all k entries
                 const unsigned long long ck = ((unsigned long long)f2key_tc(sc) << 32) | (unsigned long long)(0xffffffffu - col);
-                const int slot = (count < k) ? count++ : minpos;
-                tk[slot * TC_BM + row] = ck;
-                if (count == k) {
-                    // minimum of the k entries: four independent running minima (the compare-select chain of a single one
-                    // is what an insertion costs), merged at the end; entries are unique, so the position follows the key
-                    unsigned long long m0 = ~0ull, m1 = ~0ull, m2 = ~0ull, m3 = ~0ull;
-                    int p0 = 0, p1 = 0, p2 = 0, p3 = 0;
-                    int t = 0;
-                    for (; t + 4 <= k; t += 4) {
-                        const unsigned long long x0 = tk[(t + 0) * TC_BM + row], x1 = tk[(t + 1) * TC_BM + row];
-                        const unsigned long long x2 = tk[(t + 2) * TC_BM + row], x3 = tk[(t + 3) * TC_BM + row];
-                        if (x0 < m0) m0 = x0, p0 = t;
-                        if (x1 < m1) m1 = x1, p1 = t + 1;
-                        if (x2 < m2) m2 = x2, p2 = t + 2;
-                        if (x3 < m3) m3 = x3, p3 = t + 3;
+                auto sift_down = [&](int i, unsigned long long val) {
+                    for (;;) {
+                        const int l = 2 * i + 1;
+                        if (l >= k) break;
+                        const unsigned long long hl = tks[l * TC_BM + row];
+                        const unsigned long long hr = (l + 1 < k) ? tks[(l + 1) * TC_BM + row] : ~0ull;
+                        const bool right = hr < hl;
+                        const unsigned long long hc = right ? hr : hl;
+                        if (!(hc < val)) break;
+                        tks[i * TC_BM + row] = hc;
+                        i = right ? l + 1 : l;
                     }
-                    for (; t < k; ++t) {
-                        const unsigned long long x0 = tk[t * TC_BM + row];
-                        if (x0 < m0) m0 = x0, p0 = t;
+                    tks[i * TC_BM + row] = val;
+                };
+                bool full = false;
+                if (count < k) {
+                    tks[count * TC_BM + row] = ck;
+                    if (++count == k) {
+                        for (int s0 = k / 2 - 1; s0 >= 0; --s0) sift_down(s0, tks[s0 * TC_BM + row]);
+                        full = true;
                     }
-                    if (m1 < m0) m0 = m1, p0 = p1;
-                    if (m3 < m2) m2 = m3, p2 = p3;
-                    if (m2 < m0) m0 = m2, p0 = p2;
-                    minpos = p0;
-                    thr = key2f_tc((uint32_t)(m0 >> 32));
+                } else {
+                    sift_down(0, ck);  // (ck beats the root: its score is above the threshold, which is at least the root's)
+                    full = true;
+                }
+                if (full) {
+                    const float othr = key2f_tc((uint32_t)(tks[row] >> 32));
+                    if (ES == 2) s_thr[set * TC_BM + row] = othr;
+                    thr = fmaxf(othr, pthr);
                 }
             }
             nbuf = 0;
@@ -339,18 +447,22 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
         float *wbeta = sbeta + (warp - 2) * TC_BN;
         float4 bnext = *reinterpret_cast<const float4 *>(p.beta + 4 * lane);
         for (int32_t nt = 0; nt < n_tiles; ++nt) {
-            const uint32_t acc = (uint32_t)nt % TC_ACC;
+            const uint32_t acc = (uint32_t)nt % NACC;
             __syncwarp();  // (every lane is done with the previous tile's values)
             *reinterpret_cast<float4 *>(wbeta + 4 * lane) = bnext;
             if (nt + 1 < n_tiles) bnext = *reinterpret_cast<const float4 *>(p.beta + (size_t)(nt + 1) * TC_BN + 4 * lane);
             __syncwarp();
+            if (ES == 2) {  // the other half's k-th best is a lower bound of the row's, too (monotone: a stale value is still valid)
+                pthr = fmaxf(pthr, s_thr[(set ^ 1) * TC_BM + row]);
+                thr = fmaxf(thr, pthr);
+            }
             // a tile boundary is where a warp drains (one round per parked survivor of its fullest row)
-            if (__ballot_sync(0xffffffffu, nbuf > MFK_TC_SOFT) != 0u) drain();
-            mbar_wait(acc_full + acc, ((uint32_t)nt / TC_ACC) & 1u);
+            if (__ballot_sync(0xffffffffu, nbuf > SOFTV) != 0u) drain();
+            mbar_wait(acc_full + acc, ((uint32_t)nt / NACC) & 1u);
             tc_fence_after();
-            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + acc * TC_BN;
+            const uint32_t taddr = tmem_base + ((uint32_t)(quad * 32) << 16) + ACC_COL0 + acc * TC_BN;
 #pragma unroll 1
-            for (int ch = 0; ch < TC_BN / 32; ++ch) {
+            for (int ch = set * (TC_BN / 32 / ES); ch < (set + 1) * (TC_BN / 32 / ES); ++ch) {
                 uint32_t v[32];
                 asm volatile(
                     "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
@@ -402,7 +514,7 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                 for (int half = 0; half < 2; ++half) {
                     const uint32_t hc = (p.debug & 8) ? 0u : (cand >> (16 * half)) & 0xffffu;
                     if (__ballot_sync(0xffffffffu, hc != 0u) == 0u) continue;  // (warp-uniform)
-                    if (__ballot_sync(0xffffffffu, nbuf > TC_CAP - 16) != 0u) drain();  // (rare: the drains at tile boundaries come first)
+                    if (__ballot_sync(0xffffffffu, nbuf > CAPV - 16) != 0u) drain();  // (rare: the drains at tile boundaries come first)
                     // slot of survivor j = nbuf + survivors before it: no dependent chain through the counter; groups of four
                     // columns without a survivor in any lane are skipped
                     const uint32_t wany = __reduce_or_sync(0xffffffffu, hc);
@@ -413,7 +525,7 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                         for (int j = 4 * g; j < 4 * g + 4; ++j) {
                             if ((hc >> j) & 1u) {
                                 const int slot = nbuf + __popc(hc & ((1u << j) - 1u));
-                                sbuf[slot * TC_BM + row] = ((unsigned long long)v[16 * half + j] << 32) | (unsigned long long)(uint32_t)(col0 + 16 * half + j);
+                                sbufs[slot * TC_BM + row] = ((unsigned long long)v[16 * half + j] << 32) | (unsigned long long)(uint32_t)(col0 + 16 * half + j);
                             }
                         }
                     }
@@ -427,22 +539,39 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
         // ---- winners -> predictions: insertion-sort the row's buffer (descending), then emit
         if (live) {
             for (int i = 1; i < count; ++i) {
-                const unsigned long long x = tk[i * TC_BM + row];
+                const unsigned long long x = tks[i * TC_BM + row];
                 int j = i - 1;
-                while (j >= 0 && tk[j * TC_BM + row] < x) {
-                    tk[(j + 1) * TC_BM + row] = tk[j * TC_BM + row];
+                while (j >= 0 && tks[j * TC_BM + row] < x) {
+                    tks[(j + 1) * TC_BM + row] = tks[j * TC_BM + row];
                     --j;
                 }
-                tk[(j + 1) * TC_BM + row] = x;
+                tks[(j + 1) * TC_BM + row] = x;
             }
+        }
+        int countB = 0, ia = 0, ib = 0;  // ES = 2: the two sorted lists of a row are merged by the first set's thread
+        if (ES == 2) {
+            if (set == 1) s_cnt[row] = count;
+            asm volatile("bar.sync %0, 64;" ::"r"(3 + quad) : "memory");  // the two warps of this quarter of the rows
+            if (set == 0) countB = s_cnt[row];
+        }
+        if (live && set == 0) {
+            const unsigned long long *tkb = tk + KR * TC_BM;
             const int32_t user = p.users[m0 + row];
             const float ub = (p.kernel == MFK_KERNEL_RBF) ? 0.f : p.bu[user];
-            const float un = (p.kernel == MFK_KERNEL_RBF) ? p.unorm[m0 + row] : 0.f;
+            const float un = (p.kernel == MFK_KERNEL_RBF) ? (TS ? un_row : p.unorm[m0 + row]) : 0.f;
             for (int j = 0; j < k; ++j) {
                 float score = -INFINITY;
                 int32_t item = -1;
-                if (j < count) {
-                    const unsigned long long ck = tk[j * TC_BM + row];
+                if (j < count + countB) {
+                    unsigned long long ck;
+                    if (ES == 2) {  // the larger head of the two lists (keys are unique)
+                        const unsigned long long ka = ia < count ? tks[ia * TC_BM + row] : 0ull;
+                        const unsigned long long kb2 = ib < countB ? tkb[ib * TC_BM + row] : 0ull;
+                        if (ka > kb2) ck = ka, ++ia;
+                        else ck = kb2, ++ib;
+                    } else {
+                        ck = tks[j * TC_BM + row];
+                    }
                     item = (int32_t)(0xffffffffu - (uint32_t)(ck & 0xffffffffull));
                     const float kv = key2f_tc((uint32_t)(ck >> 32));
                     if (p.kernel == MFK_KERNEL_LINEAR) score = p.mu + ub + kv;
@@ -533,18 +662,33 @@ int score_tc(int kernel, const int32_t *d_users, int64_t m, const float *d_P, co
     if (rc) return rc;
 
     const size_t smem = 1024 + (size_t)TC_STAGES * TC_STAGE_BYTES + (size_t)TC_KCAP * TC_BM * 8 + 4 * TC_BN * 4 +
-                        (size_t)TC_CAP * TC_BM * 8 + 128;
-    MFK_CUDA(cudaFuncSetAttribute(k_score_tc, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+                        (size_t)TC_CAP * TC_BM * 8 + 3 * TC_BM * 4 + 192;
+    // rows of up to 128 floats: the user tile lives in tensor memory (MFK_SCORE_TS=0 keeps it in shared memory)
+    const char *ts_env = getenv("MFK_SCORE_TS");
+    const bool ts = kp <= TC_BN && !(ts_env && ts_env[0] == '0');
+    // ... and with k small enough for two lists per row next to two stages, eight epilogue warps (MFK_SCORE_ES=1: four)
+    const size_t smem2 = 1024 + (size_t)TC_STAGES * (TC_STAGE_BYTES / 2) + 2 * (size_t)k * TC_BM * 8 + 8 * TC_BN * 4 +
+                         2 * (size_t)24 * TC_BM * 8 + 3 * TC_BM * 4 + 192;
+    const char *es_env = getenv("MFK_SCORE_ES");
+    DeviceProps props;
+    rc = device_props(&props);
+    if (rc) return rc;
+    const bool es2 = ts && smem2 <= props.smem_optin && !(es_env && es_env[0] == '1');
+    MFK_CUDA(cudaFuncSetAttribute(k_score_tc<false, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MFK_CUDA(cudaFuncSetAttribute(k_score_tc<true, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    MFK_CUDA(cudaFuncSetAttribute(k_score_tc<true, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem2));
     for (int64_t u0 = 0; u0 < m; u0 += TC_USER_CHUNK) {
         const int64_t mt = (m - u0 < TC_USER_CHUNK) ? (m - u0) : TC_USER_CHUNK;
         const int64_t mp = round_up(mt, TC_BM);
-        k_split_rows<<<(unsigned)((mp * 32 + 255) / 256), 256, 0, st>>>(d_P, ld, n_factors, d_users + u0, (int32_t)mt,
-                                                                       (int32_t)mp, kp, uhi, ulo, unorm);
-        MFK_LAUNCH_CHECK();
-        CUtensorMap tm_uhi, tm_ulo;
-        rc = make_tmap(&tm_uhi, uhi, mp, kp);
-        if (rc == MFK_OK) rc = make_tmap(&tm_ulo, ulo, mp, kp);
-        if (rc) return rc;
+        CUtensorMap tm_uhi = tm_qhi, tm_ulo = tm_qlo;  // (TS: not used)
+        if (!ts) {
+            k_split_rows<<<(unsigned)((mp * 32 + 255) / 256), 256, 0, st>>>(d_P, ld, n_factors, d_users + u0, (int32_t)mt,
+                                                                           (int32_t)mp, kp, uhi, ulo, unorm);
+            MFK_LAUNCH_CHECK();
+            rc = make_tmap(&tm_uhi, uhi, mp, kp);
+            if (rc == MFK_OK) rc = make_tmap(&tm_ulo, ulo, mp, kp);
+            if (rc) return rc;
+        }
         TcParams p;
         p.m = (int32_t)mt;
         p.n_items = n_items;
@@ -565,13 +709,18 @@ int score_tc(int kernel, const int32_t *d_users, int64_t m, const float *d_P, co
         p.lo = lo;
         p.hi = hi;
         p.bound = bound;
+        p.P = d_P;
+        p.ldP = ld;
+        p.F = n_factors;
         {
             const char *e = getenv("MFK_TC_DEBUG");
             p.debug = e ? atoi(e) : 0;
         }
         p.out_scores = d_scores + (size_t)u0 * k;
         p.out_items = d_items + (size_t)u0 * k;
-        k_score_tc<<<(unsigned)(mp / TC_BM), TC_THREADS, smem, st>>>(tm_uhi, tm_ulo, tm_qhi, tm_qlo, p);
+        if (es2) k_score_tc<true, 2><<<(unsigned)(mp / TC_BM), 64 + 128 * 2, smem2, st>>>(tm_uhi, tm_ulo, tm_qhi, tm_qlo, p);
+        else if (ts) k_score_tc<true, 1><<<(unsigned)(mp / TC_BM), TC_THREADS, smem, st>>>(tm_uhi, tm_ulo, tm_qhi, tm_qlo, p);
+        else k_score_tc<false, 1><<<(unsigned)(mp / TC_BM), TC_THREADS, smem, st>>>(tm_uhi, tm_ulo, tm_qhi, tm_qlo, p);
         MFK_LAUNCH_CHECK();
     }
     return MFK_OK;
