@@ -76,6 +76,11 @@ struct mfk_plan {
     // and items exchanged (swapped = 1: su holds item ids, si user ids, the workers own users)
     mfk_plan *hot_users = nullptr;
     int32_t n_hot_users = 0, swapped = 0;
+    // hot_parallel = 1: no rating of a hot item by a hot user is in `hot` (they are part of this plan), the two hot phases touch
+    // disjoint rows and run side by side -- `hot_users` on aux_stream between the two events
+    int32_t hot_parallel = 0;
+    cudaStream_t aux_stream = nullptr;
+    cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
     uint32_t phases = 7;  // diagnostics: bit 0 hot items, bit 1 hot users, bit 2 the rest (mfk_plan_set_phases)
     int64_t n_total = 0;
     int32_t n_hot_items = 0;

@@ -1053,7 +1053,26 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
     prm.upd_user = update_user_params ? 1 : 0;
     prm.upd_item = update_item_params ? 1 : 0;
     int rc;
-    if (plan->hot && plan->hot->n > 0 && (plan->phases & 1u)) {
+    // The two hot phases side by side (the plan kept their rows disjoint): the hot-user launch goes to a second stream between
+    // a fork and a join event, the hot-item launch stays on the caller's stream.  Both are cooperative launches whose workers
+    // add up to the SM count at most, so they are resident together; neither waits for the other.
+    const bool fork = plan->hot_parallel && plan->hot && plan->hot->n > 0 && plan->hot_users && plan->hot_users->n > 0 &&
+                      (plan->phases & 3u) == 3u;
+    cudaStream_t st_main = st;
+    if (fork) {
+        if (!plan->aux_stream) {
+            MFK_CUDA(cudaStreamCreateWithFlags(&plan->aux_stream, cudaStreamNonBlocking));
+            MFK_CUDA(cudaEventCreateWithFlags(&plan->ev_fork, cudaEventDisableTiming));
+            MFK_CUDA(cudaEventCreateWithFlags(&plan->ev_join, cudaEventDisableTiming));
+        }
+        MFK_CUDA(cudaEventRecord(plan->ev_fork, st_main));
+        MFK_CUDA(cudaStreamWaitEvent(plan->aux_stream, plan->ev_fork, 0));
+    }
+    for (int pass = 0; pass < 2; ++pass) {
+    // (pass 0: the hot-user phase when it goes to the second stream, pass 1: everything else in the usual order)
+    if (pass == 0 && !fork) continue;
+    st = (pass == 0) ? plan->aux_stream : st_main;
+    if (pass == 1 && plan->hot && plan->hot->n > 0 && (plan->phases & 1u)) {
         // hot phase first: the most-rated items, one CTA each (exact mini-batches for the linear kernel; the
         // other kernels walk the same sub-plan with the ring kernel, one warp per item)
         mfk_plan *hot = plan->hot;
@@ -1068,7 +1087,7 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         else rc = launch_ring_nv<MFK_KERNEL_RBF>(hot, hp, st);
         if (rc) return rc;
     }
-    if (plan->hot_users && plan->hot_users->n > 0 && (plan->phases & 2u)) {
+    if ((pass == 0) == fork && plan->hot_users && plan->hot_users->n > 0 && (plan->phases & 2u)) {
         // then the most active users: the update rules are symmetric in (p_u, b_u) <-> (q_i, b_i), so the same
         // kernels run on the role-swapped sub-plan with the parameter arrays exchanged
         mfk_plan *hu = plan->hot_users;
@@ -1082,7 +1101,11 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         else if (kernel == MFK_KERNEL_SIGMOID) rc = launch_ring_nv<MFK_KERNEL_SIGMOID>(hu, hp, st);
         else rc = launch_ring_nv<MFK_KERNEL_RBF>(hu, hp, st);
         if (rc) return rc;
+        if (pass == 0) MFK_CUDA(cudaEventRecord(plan->ev_join, plan->aux_stream));
     }
+    }
+    st = st_main;
+    if (fork) MFK_CUDA(cudaStreamWaitEvent(st_main, plan->ev_join, 0));
     if (plan->n == 0 || !(plan->phases & 4u)) return MFK_OK;
     prm.base = next_base(plan, st, &rc);
     if (rc) return rc;

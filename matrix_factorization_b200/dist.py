@@ -164,14 +164,16 @@ class DsgdTrainer:
 
 
 def sharded_topk(kernel, users, P, bu, Q_local, bi_local, local_to_global, n_factors, mu, gamma, lo, hi, k, bound,
-                 mask_ptr=None, mask_items_global=None, global_to_local=None, group=None):
+                 mask_ptr=None, mask_items_global=None, global_to_local=None, group=None, mask_local=None):
     """
     Item-sharded recommend: every rank scores ALL requested users against ITS item
     stripe (local top-k with the known-item mask restricted to the stripe), the per-rank lists are
     all-gathered and merged (score desc, ties by lower global item id), then clipped.
     users int32 [m] (global user ids, P / bu replicated); Q_local [n_local, ld]; local_to_global int32
     [n_local]; mask in CSR form over GLOBAL item ids with global_to_local int32 [n_items] (-1 = not
-    on this rank).  Returns (scores [m, k], items [m, k] global ids) on every rank.
+    on this rank); or mask_local = (ptr int64 [m + 1], local item ids int32, ascending inside a row) when the caller
+    keeps the stripe's part of the known-item lists (a rank of the DSGD grid does).  Returns (scores [m, k], items
+    [m, k] global ids) on every rank.
     """
     import torch
     import torch.distributed as dist
@@ -181,7 +183,9 @@ def sharded_topk(kernel, users, P, bu, Q_local, bi_local, local_to_global, n_fac
     n_local = int(Q_local.shape[0])
     k_loc = max(1, min(k, n_local))
     mp = mi = None
-    if mask_ptr is not None:
+    if mask_local is not None:
+        mp, mi = mask_local
+    elif mask_ptr is not None:
         loc = global_to_local[mask_items_global.long()]
         keep = loc >= 0
         # rows keep their CSR structure: count kept entries per row

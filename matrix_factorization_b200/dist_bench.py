@@ -58,7 +58,19 @@ def run(args):
     items_per_stripe = torch.bincount(is_, minlength=G).cpu().tolist()
     mu = float(wl["r"].double().mean().item())
     n_local = int(u_loc.numel())
-    del wl["u"], wl["i"], wl["r"], mine, it
+    # item-sharded recommend: the known-item lists of ALL users restricted to this rank's item stripe (local item ids,
+    # CSR built on the GPU), and every user's row in the gathered user matrix (stripe-major, stripes padded alike)
+    in_stripe = is_[wl["i"].long()] == rank
+    csr = engine.Csr(wl["u"][in_stripe], il[wl["i"][in_stripe].long()].int(), wl["r"][in_stripe], U, items_per_stripe[rank])
+    rec_ptr, rec_col, *_ = csr.export()
+    rec_ptr, rec_col = rec_ptr.clone(), rec_col.clone()
+    csr.close()
+    max_users = int(torch.bincount(us, minlength=G).max().item())
+    rec_rows = (us * max_users + ul).int().contiguous()
+    stripe_items = torch.nonzero(is_ == rank).flatten()
+    local_to_global = torch.empty(items_per_stripe[rank], dtype=torch.int32, device=dev)
+    local_to_global[il[stripe_items]] = stripe_items.int()
+    del wl["u"], wl["i"], wl["r"], mine, it, in_stripe
     torch.cuda.empty_cache()
 
     ld = engine.round_up4(F)
@@ -146,6 +158,39 @@ def run(args):
     dist.all_reduce(e2e_t, op=dist.ReduceOp.MAX)
     e2e_s = float(e2e_t.item())
 
+    # ---- recommend, item-sharded: all-gather of the user stripes, every rank scores all users against its item
+    #      stripe (known items of the stripe masked), all-gather of the per-rank lists, merge
+    from .dist import sharded_topk
+
+    k_rec = 50
+    Ps = torch.zeros(max_users, ld, device=dev)  # this rank's users, padded to the longest stripe
+    Ps[:n_users_local] = dP
+    bs = torch.zeros(max_users, device=dev)
+    bs[:n_users_local] = dbu
+    Pall = torch.empty(G * max_users, ld, device=dev)
+    ball = torch.empty(G * max_users, device=dev)
+    rec_ms = []
+    rec_out = None
+    for rep_ in range(3):
+        torch.cuda.synchronize()
+        dist.barrier()
+        ra, rb = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        ra.record()
+        dist.all_gather_into_tensor(Pall.view(-1), Ps.view(-1))
+        dist.all_gather_into_tensor(ball, bs)
+        rec_out = sharded_topk("linear", rec_rows, Pall, ball, qs, bis, local_to_global, F, mu, gamma, 0.0, 5.0, k_rec, True,
+                               mask_local=(rec_ptr, rec_col))
+        rb.record()
+        torch.cuda.synchronize()
+        t = torch.tensor([ra.elapsed_time(rb)], device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        if rep_ > 0:
+            rec_ms.append(float(t.item()))
+    rec = {"metric": "recommend users/s", "value": U / (min(rec_ms) * 1e-3), "unit": "users/s", "users": U, "k": k_rec,
+           "ms": min(rec_ms), "mask": "each user's training items",
+           "path": f"item-sharded over {G} GPUs: all-gather of the user stripes, local tcgen05 top-{k_rec} per item stripe, "
+                   "all-gather of the lists, mfk_topk_merge"}
+
     if rank == 0:
         peak, peak_src = bench.load_peaks()
         bpu = 16 * F + 28
@@ -170,6 +215,7 @@ def run(args):
                     "d2h_bytes_per_step": int((n_users_local + items_per_stripe[0]) * (ld + 1) * 4),
                     "call": f"per rank: pinned host shard -> H2D -> {G} block plans -> {wl['n_epochs']} DSGD epochs + RMSE -> D2H",
                     "seconds_per_call": e2e_s, "train_rmse_last": e2e_rmse},
+            "recommend": rec,
             "gpu_launches": int(args.steps * (G + 2 * G)),
             "clocks": clk,
         }
