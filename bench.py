@@ -380,7 +380,9 @@ def run_ours_single(args):
                      "traffic_note": "measured dram__bytes_read+write of ONE launch of the dominant kernel (ncu --set full, "
                                      "profiles/r02_ncu_full_summary.txt); achieved/frac are algorithmic bytes / time and overstate "
                                      "HBM use (item rows live in shared memory, user rows mostly in L2)",
-                     "kernel": "one epoch = " + " + ".join(ph["kernel"] for ph in phases),
+                     "kernel": "one epoch = " + " + ".join(ph["kernel"] for ph in phases) + (
+                         " -- the two k_sgd_batch launches run SIDE BY SIDE on two streams (disjoint rows, their workers share "
+                         "the SMs): kernel_ms is the whole epoch, per_kernel times each launch alone" if info.get("hot_parallel") else ""),
                      "kernel_ms": sgd_ms, "dominant": dominant, "per_kernel": phases, "bytes_per_update": bytes_per_update,
                      "peak_source": peak_src, "frac_of_nominal_8TBs": achieved / 8000.0, "ring_stats": ring_stats},
         "cpu_baseline": {"value": cpu_v, "unit": "rating-updates/s", "cores": 1, "kind": "port",

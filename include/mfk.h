@@ -101,7 +101,7 @@ typedef struct {
     int32_t n_hot_workers;      /* CTAs of the hot-item sub-plan (each owns up to hot_max_slots items) */
     int32_t n_hot_user_workers; /* CTAs of the hot-user sub-plan */
     int32_t hot_max_slots;
-    int32_t reserved2;
+    int32_t hot_parallel;        /* 1: the hot-item and the hot-user phase touch disjoint rows and run side by side (two streams) */
 } mfk_plan_info;
 
 /* d_u/d_i/d_r: the n ratings as internal ids (0..n_users-1 / 0..n_items-1).  Synchronises

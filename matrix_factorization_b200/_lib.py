@@ -35,7 +35,7 @@ class PlanInfo(C.Structure):
                 ("n_hot_items", C.c_int32), ("n_steps", C.c_int32), ("n_hot_ratings", C.c_int64),
                 ("n_hot_users", C.c_int32), ("flat", C.c_int32), ("n_hot_user_ratings", C.c_int64),
                 ("n_hot_workers", C.c_int32), ("n_hot_user_workers", C.c_int32), ("hot_max_slots", C.c_int32),
-                ("reserved2", C.c_int32)]
+                ("hot_parallel", C.c_int32)]
 
     def as_dict(self):
         return {f: getattr(self, f) for f, _ in self._fields_}
