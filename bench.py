@@ -42,8 +42,8 @@ WORKLOADS = {
 
 # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu captures (bytes); None = not captured
 # (profiles/r02_ncu_full_summary.txt: ML-20M shape, one launch each)
-KNOWN_DRAM_TRAFFIC = {("ml-20m", "k_sgd_batch (hot items)"): 219774208 + 525198592,
-                      ("ml-20m", "k_sgd_flat (the rest)"): 266747648 + 468194048}
+KNOWN_DRAM_TRAFFIC = {("ml-20m", "k_sgd_batch (hot items)"): 219262976 + 538206720,
+                      ("ml-20m", "k_sgd_flat (the rest)"): 268506112 + 472398592}
 
 
 def load_peaks():
@@ -378,7 +378,7 @@ def run_ours_single(args):
         "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                      "traffic": KNOWN_DRAM_TRAFFIC.get((args.workload, dominant)),
                      "traffic_note": "measured dram__bytes_read+write of ONE launch of the dominant kernel (ncu --set full, "
-                                     "profiles/r02_ncu_full_summary.txt); achieved/frac are algorithmic bytes / time and overstate "
+                                     "profiles/r02b_ncu_full_summary.txt); achieved/frac are algorithmic bytes / time and overstate "
                                      "HBM use (item rows live in shared memory, user rows mostly in L2)",
                      "kernel": "one epoch = " + " + ".join(ph["kernel"] for ph in phases) + (
                          " -- the two k_sgd_batch launches run SIDE BY SIDE on two streams (disjoint rows, their workers share "

@@ -103,15 +103,15 @@ def test_hot_phases_side_by_side_and_one_after_the_other(parallel, monkeypatch):
     phases touch disjoint rows) against the same plan run phase after phase (MFK_HOT_PARALLEL=0): both must reproduce
     the oracle's replay of the order they emit, with every update-flag combination, and say which mode they are in."""
     monkeypatch.setenv("MFK_HOT_PARALLEL", parallel)
-    U, I, N, F = 3000, 1200, 400_000, 128
-    u, i, r, rng = _skewed(77, U, I, N, n_hot_items=3, hot_share=0.3, n_hot_users=5, user_share=0.1)
-    info = _info(u, i, r, U, I, F, hot_min_degree=2000)
+    U, I, N, F = 20_000, 3000, 400_000, 128
+    u, i, r, rng = _skewed(77, U, I, N, n_hot_items=3, hot_share=0.1, n_hot_users=5, user_share=0.03)
+    info = _info(u, i, r, U, I, F, hot_min_degree=1000)
     assert info["n_hot_items"] >= 3 and info["n_hot_users"] >= 3, info
     assert info["hot_parallel"] == int(parallel), info
     if parallel == "1":
         assert info["n_hot_workers"] + info["n_hot_user_workers"] <= 148, info
     _run_and_replay(u, i, r, rng, U, I, F, 0.002, 0.02, [(True, True), (True, False), (False, True)],
-                    dict(hot_min_degree=2000), epochs=2)
+                    dict(hot_min_degree=1000), epochs=2)
 
 
 @pytest.mark.parametrize("lr,reg", [(0.01, 1.0), (0.05, 15.0), (0.1, 10.0), (0.06, 20.0), (0.05, 0.0)])
