@@ -53,7 +53,7 @@ def run(workload="netflix", users=32768, k=50, kernel="linear", reps=3, mask_per
             "path": "simt" if os.environ.get("MFK_SCORE_SIMT") == "1" or k > 64 else "tcgen05 split-TF32"}
 
 
-def run_workload(wl, k=50, kernel="linear", reps=2, seed=1, cpu_users=1000):
+def run_workload(wl, k=50, kernel="linear", reps=3, seed=1, cpu_users=1000):
     """recommend for ALL users of a bench workload (bench.gen_workload dict): top-k with each user's TRAINING items as the
     known-item mask (CSR built on the GPU by mfk_csr_create) -- the second half of BASELINE.json's metric.  Next to it the
     reference-equivalent per-user loop on the host (predict all candidates, mask, sort, head: recommender_base.py:245-266)
