@@ -1068,41 +1068,36 @@ extern "C" int mfk_kmf_sgd_epoch(mfk_plan *plan, int kernel, float *d_P, float *
         MFK_CUDA(cudaEventRecord(plan->ev_fork, st_main));
         MFK_CUDA(cudaStreamWaitEvent(plan->aux_stream, plan->ev_fork, 0));
     }
-    for (int pass = 0; pass < 2; ++pass) {
-    // (pass 0: the hot-user phase when it goes to the second stream, pass 1: everything else in the usual order)
-    if (pass == 0 && !fork) continue;
-    st = (pass == 0) ? plan->aux_stream : st_main;
-    if (pass == 1 && plan->hot && plan->hot->n > 0 && (plan->phases & 1u)) {
-        // hot phase first: the most-rated items, one CTA each (exact mini-batches for the linear kernel; the
-        // other kernels walk the same sub-plan with the ring kernel, one warp per item)
-        mfk_plan *hot = plan->hot;
-        SgdParams hp = prm;
-        hp.base = next_base(hot, st, &rc);
+    // one hot sub-plan on a stream: exact mini-batches for the linear kernel (k_sgd_batch); the other kernels walk the same
+    // sub-plan with the ring kernel, one warp per id
+    auto launch_hot_phase = [&](mfk_plan *sub, SgdParams hp, cudaStream_t s) -> int {
+        int rc2 = MFK_OK;
+        hp.base = next_base(sub, s, &rc2);
+        if (rc2) return rc2;
+        if (batch_engine_ok(kernel, hp) && use_batch_engine()) return launch_batch(sub, hp, s);
+        if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128 && sub->max_slots == 1 && legacy_hot_ok(hp))
+            return use_hot_pipe() ? launch_hot_pipe<1>(sub, hp, s) : launch_hot<1>(sub, hp, s);
+        if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256 && sub->max_slots == 1 && legacy_hot_ok(hp)) return launch_hot<2>(sub, hp, s);
+        if (kernel == MFK_KERNEL_LINEAR) return launch_ring_nv<MFK_KERNEL_LINEAR>(sub, hp, s);
+        if (kernel == MFK_KERNEL_SIGMOID) return launch_ring_nv<MFK_KERNEL_SIGMOID>(sub, hp, s);
+        return launch_ring_nv<MFK_KERNEL_RBF>(sub, hp, s);
+    };
+    const bool run_items = plan->hot && plan->hot->n > 0 && (plan->phases & 1u);
+    const bool run_users = plan->hot_users && plan->hot_users->n > 0 && (plan->phases & 2u);
+    if (fork) {  // (hot users first: their launch goes to the second stream and the hot items follow at once on the caller's)
+        rc = launch_hot_phase(plan->hot_users, swap_roles(prm, plan->hot_users), plan->aux_stream);
         if (rc) return rc;
-        if (batch_engine_ok(kernel, hp) && use_batch_engine()) rc = launch_batch(hot, hp, st);
-        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128 && hot->max_slots == 1 && legacy_hot_ok(hp)) rc = use_hot_pipe() ? launch_hot_pipe<1>(hot, hp, st) : launch_hot<1>(hot, hp, st);
-        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256 && hot->max_slots == 1 && legacy_hot_ok(hp)) rc = launch_hot<2>(hot, hp, st);
-        else if (kernel == MFK_KERNEL_LINEAR) rc = launch_ring_nv<MFK_KERNEL_LINEAR>(hot, hp, st);
-        else if (kernel == MFK_KERNEL_SIGMOID) rc = launch_ring_nv<MFK_KERNEL_SIGMOID>(hot, hp, st);
-        else rc = launch_ring_nv<MFK_KERNEL_RBF>(hot, hp, st);
+        MFK_CUDA(cudaEventRecord(plan->ev_join, plan->aux_stream));
+    }
+    if (run_items) {  // the most-rated items, one CTA per worker
+        rc = launch_hot_phase(plan->hot, prm, st_main);
         if (rc) return rc;
     }
-    if ((pass == 0) == fork && plan->hot_users && plan->hot_users->n > 0 && (plan->phases & 2u)) {
+    if (run_users && !fork) {
         // then the most active users: the update rules are symmetric in (p_u, b_u) <-> (q_i, b_i), so the same
         // kernels run on the role-swapped sub-plan with the parameter arrays exchanged
-        mfk_plan *hu = plan->hot_users;
-        SgdParams hp = swap_roles(prm, hu);
-        hp.base = next_base(hu, st, &rc);
+        rc = launch_hot_phase(plan->hot_users, swap_roles(prm, plan->hot_users), st_main);
         if (rc) return rc;
-        if (batch_engine_ok(kernel, hp) && use_batch_engine()) rc = launch_batch(hu, hp, st);
-        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 128 && hu->max_slots == 1 && legacy_hot_ok(hp)) rc = use_hot_pipe() ? launch_hot_pipe<1>(hu, hp, st) : launch_hot<1>(hu, hp, st);
-        else if (kernel == MFK_KERNEL_LINEAR && prm.F <= 256 && hu->max_slots == 1 && legacy_hot_ok(hp)) rc = launch_hot<2>(hu, hp, st);
-        else if (kernel == MFK_KERNEL_LINEAR) rc = launch_ring_nv<MFK_KERNEL_LINEAR>(hu, hp, st);
-        else if (kernel == MFK_KERNEL_SIGMOID) rc = launch_ring_nv<MFK_KERNEL_SIGMOID>(hu, hp, st);
-        else rc = launch_ring_nv<MFK_KERNEL_RBF>(hu, hp, st);
-        if (rc) return rc;
-        if (pass == 0) MFK_CUDA(cudaEventRecord(plan->ev_join, plan->aux_stream));
-    }
     }
     st = st_main;
     if (fork) MFK_CUDA(cudaStreamWaitEvent(st_main, plan->ev_join, 0));
