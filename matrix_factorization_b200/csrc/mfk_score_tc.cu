@@ -350,8 +350,8 @@ k_score_tc(const __grid_constant__ CUtensorMap tm_uhi, const __grid_constant__ C
                 for (int c4 = 0; c4 < 8; ++c4) {
                     const int c = c0 + 4 * c4;
                     float4 x = make_float4(0.f, 0.f, 0.f, 0.f);
-                    if (live && c < p.F) x = __ldg(reinterpret_cast<const float4 *>(prow + c));  // (padding columns of a row are zero)
-                    const float xs[4] = {x.x, x.y, x.z, x.w};
+                    if (live && c < p.F) x = __ldg(reinterpret_cast<const float4 *>(prow + c));  // (ld is a multiple of 4: inside the row)
+                    const float xs[4] = {x.x, c + 1 < p.F ? x.y : 0.f, c + 2 < p.F ? x.z : 0.f, c + 3 < p.F ? x.w : 0.f};  // (columns beyond F do not count)
 #pragma unroll
                     for (int e = 0; e < 4; ++e) {
                         uint32_t hb;
