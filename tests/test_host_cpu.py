@@ -28,6 +28,21 @@ def test_cabi_exports_every_declared_symbol():
     assert L.mfk_abi_version() == 1
 
 
+def test_cabi_structs_match_the_ctypes_mirrors():
+    """Field by field: mfk_plan_opts / mfk_plan_info of include/mfk.h against the ctypes structures of _lib (names, order, widths)."""
+    import ctypes as C
+
+    hdr = open(os.path.join(ROOT, "include", "mfk.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    widths = {"int32_t": C.c_int32, "uint32_t": C.c_uint32, "int64_t": C.c_int64}
+    for cname, mirror in (("mfk_plan_opts", _lib.PlanOpts), ("mfk_plan_info", _lib.PlanInfo)):
+        body = re.search(r"typedef struct[^{]*\{([^}]*)\}\s*" + cname + r"\s*;", hdr, flags=re.S).group(1)
+        fields = []
+        for ctype, names in re.findall(r"\b(u?int(?:32|64)_t)\s+([^;]+);", body):
+            fields += [(n.strip(), widths[ctype]) for n in names.split(",")]
+        assert fields == list(mirror._fields_), (cname, fields, mirror._fields_)
+
+
 def test_constructor_defaults_and_errors():
     m = mfb.KernelMF()
     assert (m.n_factors, m.n_epochs, m.kernel, m.reg, m.lr, m.init_mean, m.init_sd) == (100, 100, "linear", 1, 0.01, 0, 0.1)
